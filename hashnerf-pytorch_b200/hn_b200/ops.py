@@ -1,0 +1,328 @@
+"""Tensor-level wrappers over the C ABI (include/hashnerf_b200.h).
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only: every function
+below marshals ``data_ptr()``/shape/stride plus the current CUDA stream into one C call.  There
+is no alternative implementation: CPU tensors are rejected with a RuntimeError.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+MLP_PARAMS = 9344
+MLP_SHAPES = ((64, 32), (16, 64), (64, 31), (64, 64), (3, 64))  # W0..W4, nn.Linear.weight layout
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "hashnerf_b200 runs on CUDA (sm_100a) only: got a tensor on "
+                f"{t.device}; there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} and {t.device}")
+    if dev is None:
+        raise RuntimeError("no tensor argument")
+    return dev
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _on:
+    """Make ``device`` current for the duration of a C call (no-op when it already is)."""
+
+    def __init__(self, device: torch.device):
+        self.guard = None if device.index in (None, torch.cuda.current_device()) else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+
+
+def _consecutive(tensors: Sequence[torch.Tensor]) -> bool:
+    """True if the (contiguous, fp32) tensors sit back to back in one allocation."""
+    addr = tensors[0].data_ptr()
+    for t in tensors:
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.data_ptr() != addr:
+            return False
+        addr += t.numel() * 4
+    return True
+
+
+def pack(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    """One flat fp32 view over ``tensors`` -- zero-copy when they already are slices of one flat buffer
+    (the layout HashEmbedder / NeRFSmall allocate), otherwise a packed copy."""
+    if _consecutive(tensors):
+        n = sum(t.numel() for t in tensors)
+        return torch.as_strided(tensors[0].detach(), (n,), (1,))
+    return torch.cat([t.detach().reshape(-1).float() for t in tensors])
+
+
+# ----------------------------------------------------------------------------------------------
+# hash encoding
+# ----------------------------------------------------------------------------------------------
+def spatial_hash(coords: torch.Tensor, log2_hashmap_size: int) -> torch.Tensor:
+    """embedding/hash_encoding.py:112-128 on CUDA: int64 [..., dim] -> int64 [...]."""
+    dev = _need_cuda(coords)
+    c = coords.to(torch.int64).contiguous()
+    out = torch.empty(c.shape[:-1], dtype=torch.int64, device=dev)
+    n = out.numel()
+    with _on(dev):
+        _lib.call("hn_spatial_hash", c.data_ptr(), n, int(c.shape[-1]), int(log2_hashmap_size), out.data_ptr(),
+                  _stream())
+    return out
+
+
+def voxel_vertices(x, bbox6, resolutions, log2_hashmap_size):
+    """Parity hook: (hashed [L,N,8] int64, vmin [L,N,3], vmax [L,N,3]) for every level."""
+    dev = _need_cuda(x, bbox6, resolutions)
+    x = _f32c(x)
+    N, L = x.shape[0], resolutions.numel()
+    hashed = torch.empty(L, N, 8, dtype=torch.int64, device=dev)
+    vmin = torch.empty(L, N, 3, dtype=torch.float32, device=dev)
+    vmax = torch.empty(L, N, 3, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_voxel_vertices", x.data_ptr(), bbox6.data_ptr(), resolutions.data_ptr(), N, L,
+                  int(log2_hashmap_size), hashed.data_ptr(), vmin.data_ptr(), vmax.data_ptr(), _stream())
+    return hashed, vmin, vmax
+
+
+def hash_encode_forward(x, tables_flat, bbox6, resolutions, L, F, log2T, want_keep=True):
+    dev = _need_cuda(x, tables_flat, bbox6, resolutions)
+    x = _f32c(x)
+    N = x.shape[0]
+    out = torch.empty(N, L * F, dtype=torch.float32, device=dev)
+    keep = torch.empty(N, dtype=torch.uint8, device=dev) if want_keep else None
+    with _on(dev):
+        _lib.call("hn_hash_encode_fwd", x.data_ptr(), tables_flat.data_ptr(), bbox6.data_ptr(),
+                  resolutions.data_ptr(), N, L, F, log2T, out.data_ptr(), _ptr(keep), _stream())
+    return out, keep
+
+
+def hash_encode_backward(x, dy, bbox6, resolutions, L, F, log2T, dtables_flat):
+    """Accumulates into ``dtables_flat`` ([L * 2^T * F] fp32)."""
+    dev = _need_cuda(x, dy, bbox6, resolutions, dtables_flat)
+    x, dy = _f32c(x), _f32c(dy)
+    with _on(dev):
+        _lib.call("hn_hash_encode_bwd", x.data_ptr(), dy.data_ptr(), bbox6.data_ptr(), resolutions.data_ptr(),
+                  x.shape[0], L, F, log2T, dtables_flat.data_ptr(), _stream())
+
+
+class HashEncodeFn(torch.autograd.Function):
+    """features, keep = HashEncodeFn.apply(x, bbox6, resolutions, log2T, F, *level_tables)
+
+    ``level_tables`` are the L ``nn.Embedding.weight`` parameters ([2^T, F] each).  Autograd routes the
+    table gradient to each of them; the gradients returned are slices of ONE flat buffer filled by a
+    single scatter kernel (the reference produces 16 separate dense gradients through
+    embedding_dense_backward, hash_encoding.py:106)."""
+
+    @staticmethod
+    def forward(ctx, x, bbox6, resolutions, log2T, F, *level_tables):
+        L = len(level_tables)
+        flat = pack(level_tables)
+        out, keep = hash_encode_forward(x, flat, bbox6, resolutions, L, F, log2T)
+        ctx.save_for_backward(x, bbox6, resolutions)
+        ctx.meta = (L, F, log2T)
+        keep = keep.bool()
+        ctx.mark_non_differentiable(keep)
+        return out, keep
+
+    @staticmethod
+    def backward(ctx, dout, _dkeep):
+        x, bbox6, resolutions = ctx.saved_tensors
+        L, F, log2T = ctx.meta
+        T = 1 << log2T
+        dflat = torch.zeros(L * T * F, dtype=torch.float32, device=x.device)
+        hash_encode_backward(x, dout, bbox6, resolutions, L, F, log2T, dflat)
+        grads = dflat.view(L, T, F).unbind(0)
+        return (None, None, None, None, None) + tuple(grads)
+
+
+# ----------------------------------------------------------------------------------------------
+# spherical harmonics
+# ----------------------------------------------------------------------------------------------
+def sh_encode(dirs: torch.Tensor, degree: int) -> torch.Tensor:
+    dev = _need_cuda(dirs)
+    d = _f32c(dirs).reshape(-1, 3)
+    out = torch.empty(d.shape[0], degree * degree, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_sh_encode", d.data_ptr(), d.shape[0], int(degree), out.data_ptr(), _stream())
+    return out.reshape(*dirs.shape[:-1], degree * degree)
+
+
+# ----------------------------------------------------------------------------------------------
+# NeRFSmall
+# ----------------------------------------------------------------------------------------------
+def _rows(t: torch.Tensor, width: int) -> Tuple[torch.Tensor, int]:
+    """A 2-D fp32 view whose rows are contiguous (last stride 1); returns (tensor, row stride)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2 or t.shape[1] != width:
+        raise RuntimeError(f"expected a [N,{width}] tensor, got {tuple(t.shape)}")
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < width):
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else width)
+
+
+class MLPFn(torch.autograd.Function):
+    """out[N,4] = MLPFn.apply(enc[N,32], views[Nv,16], pts_per_view, keep|None, W0, W1, W2, W3, W4)"""
+
+    @staticmethod
+    def forward(ctx, enc, views, pts_per_view, keep, *weights):
+        dev = _need_cuda(enc, views, *weights)
+        enc_r, enc_stride = _rows(enc, 32)
+        views_r, views_stride = _rows(views, 16)
+        N = enc_r.shape[0]
+        if views_r.shape[0] * pts_per_view < N:
+            raise RuntimeError("views has too few rows for pts_per_view")
+        wflat = pack(weights)
+        keep_u8 = None if keep is None else keep.to(torch.uint8).contiguous()
+        out = torch.empty(N, 4, dtype=torch.float32, device=dev)
+        with _on(dev):
+            _lib.call("hn_mlp_fwd", enc_r.data_ptr(), enc_stride, views_r.data_ptr(), views_stride,
+                      int(pts_per_view), wflat.data_ptr(), _ptr(keep_u8), N, out.data_ptr(), _stream())
+        ctx.save_for_backward(enc_r, views_r, wflat, keep_u8 if keep_u8 is not None else torch.empty(0, device=dev))
+        ctx.meta = (enc_stride, views_stride, int(pts_per_view), keep_u8 is not None, N,
+                    ctx.needs_input_grad[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        enc_r, views_r, wflat, keep_u8 = ctx.saved_tensors
+        enc_stride, views_stride, ppv, has_keep, N, _ = ctx.meta
+        dev = enc_r.device
+        dout = _f32c(dout)
+        d_enc = torch.empty(N, 32, dtype=torch.float32, device=dev)
+        dflat = torch.zeros(MLP_PARAMS, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        ws = torch.empty(max(1, lib.hn_mlp_bwd_workspace_bytes(N) // 4), dtype=torch.float32, device=dev)
+        with _on(dev):
+            _lib.call("hn_mlp_bwd", enc_r.data_ptr(), enc_stride, views_r.data_ptr(), views_stride, ppv,
+                      wflat.data_ptr(), keep_u8.data_ptr() if has_keep else None, dout.data_ptr(), N,
+                      d_enc.data_ptr(), dflat.data_ptr(), ws.data_ptr(), _stream())
+        grads, off = [], 0
+        for (o, i) in MLP_SHAPES:
+            grads.append(dflat[off:off + o * i].view(o, i))
+            off += o * i
+        return (d_enc, None, None, None) + tuple(grads)
+
+
+# ----------------------------------------------------------------------------------------------
+# compositing
+# ----------------------------------------------------------------------------------------------
+class CompositeFn(torch.autograd.Function):
+    """rgb, disp, acc, weights, depth, entropy = CompositeFn.apply(raw, z, rays_d, noise|None, white)"""
+
+    @staticmethod
+    def forward(ctx, raw, z, rays_d, noise, white_bkgd):
+        dev = _need_cuda(raw, z, rays_d, noise)
+        raw, z, rays_d = _f32c(raw), _f32c(z), _f32c(rays_d)
+        noise = None if noise is None else _f32c(noise)
+        R, S = z.shape
+        if raw.shape != (R, S, 4):
+            raise RuntimeError(f"raw must be [R,S,4], got {tuple(raw.shape)} for z {tuple(z.shape)}")
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        rgb, disp, acc, weights, depth, ent = new(R, 3), new(R), new(R), new(R, S), new(R), new(R)
+        with _on(dev):
+            _lib.call("hn_composite_fwd", raw.data_ptr(), z.data_ptr(), rays_d.data_ptr(), _ptr(noise), R, S,
+                      int(bool(white_bkgd)), rgb.data_ptr(), disp.data_ptr(), acc.data_ptr(), weights.data_ptr(),
+                      depth.data_ptr(), ent.data_ptr(), _stream())
+        ctx.save_for_backward(raw, z, rays_d, noise if noise is not None else torch.empty(0, device=dev))
+        ctx.meta = (R, S, bool(white_bkgd), noise is not None)
+        return rgb, disp, acc, weights, depth, ent
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_disp, d_acc, d_weights, d_depth, d_ent):
+        raw, z, rays_d, noise = ctx.saved_tensors
+        R, S, white, has_noise = ctx.meta
+        g = [None if t is None else _f32c(t) for t in (d_rgb, d_disp, d_acc, d_weights, d_depth, d_ent)]
+        d_raw = torch.empty_like(raw)
+        with _on(raw.device):
+            _lib.call("hn_composite_bwd", raw.data_ptr(), z.data_ptr(), rays_d.data_ptr(),
+                      noise.data_ptr() if has_noise else None, R, S, int(white), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]),
+                      _ptr(g[3]), _ptr(g[4]), _ptr(g[5]), d_raw.data_ptr(), _stream())
+        return d_raw, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# sampling (no gradients flow through these on the reference path: z_samples is detached, :549)
+# ----------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sample_pdf(bins, weights, n_samples: int, u: Optional[torch.Tensor] = None,
+               u_det: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _need_cuda(bins, weights, u, u_det)
+    bins, weights = _f32c(bins), _f32c(weights)
+    R, nb = bins.shape
+    if weights.shape != (R, nb - 1):
+        raise RuntimeError(f"weights must be [R, nbins-1] = {(R, nb - 1)}, got {tuple(weights.shape)}")
+    if u is not None:
+        u = _f32c(u)
+        if u.shape != (R, n_samples):
+            raise RuntimeError("u must be [R, n_samples]")
+    else:
+        u_det = _f32c(u_det)
+    out = torch.empty(R, n_samples, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_sample_pdf", bins.data_ptr(), weights.data_ptr(), _ptr(u), _ptr(u_det), R, nb, int(n_samples),
+                  out.data_ptr(), _stream())
+    return out
+
+
+@torch.no_grad()
+def sort_concat_rows(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    dev = _need_cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    R = a.shape[0]
+    out = torch.empty(R, a.shape[1] + b.shape[1], dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_sort_concat_rows", a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], R, out.data_ptr(),
+                  _stream())
+    return out
+
+
+@torch.no_grad()
+def coarse_z(near, far, nf_stride: int, t_vals, t_rand, R: int, S: int, lindisp: bool) -> torch.Tensor:
+    dev = _need_cuda(near, far, t_vals, t_rand)
+    z = torch.empty(R, S, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_coarse_z", near.data_ptr(), far.data_ptr(), int(nf_stride), t_vals.data_ptr(), _ptr(t_rand),
+                  R, S, int(bool(lindisp)), z.data_ptr(), _stream())
+    return z
+
+
+@torch.no_grad()
+def ray_points(rays_o, rays_d, ray_stride: int, z) -> torch.Tensor:
+    dev = _need_cuda(rays_o, rays_d, z)
+    R, S = z.shape
+    pts = torch.empty(R, S, 3, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_ray_points", rays_o.data_ptr(), rays_d.data_ptr(), int(ray_stride), z.data_ptr(), R, S,
+                  pts.data_ptr(), _stream())
+    return pts

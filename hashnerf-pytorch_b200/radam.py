@@ -1,0 +1,133 @@
+"""Rectified Adam -- drop-in for the ``RAdam`` class of the reference's ``radam.py`` (:5-94).
+
+Same constructor, defaults, param-group keys (including the ``buffer`` cache, so optimizer state dicts
+interchange with the reference's checkpoints) and per-parameter state (``step``, ``exp_avg``,
+``exp_avg_sq``).  ``step()`` differs in execution only: parameters that sit back to back in one allocation
+(the 16 hash-table levels; the five matrices of a NeRFSmall) and share hyper-parameters are updated by ONE
+fused CUDA kernel launch (hn_radam_step) instead of ~10 ATen launches per tensor.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.optim.optimizer import Optimizer
+
+from hn_b200 import _lib, ops
+
+
+class RAdam(Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, degenerated_to_sgd=False):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        self.degenerated_to_sgd = degenerated_to_sgd
+        self.grad_scale = 1.0  # set to 1/world_size by the data-parallel wrapper after a summed all-reduce
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                        buffer=[[None, None, None] for _ in range(10)])
+        super().__init__(params, defaults)
+
+    # radam.py:62-78 -- depends on the step count only
+    def _rectification(self, step, beta1, beta2):
+        beta2_t = beta2 ** step
+        n_max = 2 / (1 - beta2) - 1
+        n_sma = n_max - 2 * step * beta2_t / (1 - beta2_t)
+        if n_sma >= 5:
+            size = math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max / (n_max - 2)) \
+                / (1 - beta1 ** step)
+            return 1, size
+        if self.degenerated_to_sgd:
+            return 2, 1.0 / (1 - beta1 ** step)
+        return 0, -1.0
+
+    def _init_state(self, run):
+        """Zero moments for a run of memory-consecutive parameters, allocated as one flat buffer each."""
+        n = sum(p.numel() for p in run)
+        m = torch.zeros(n, dtype=torch.float32, device=run[0].device)
+        v = torch.zeros(n, dtype=torch.float32, device=run[0].device)
+        off = 0
+        for p in run:
+            st = self.state[p]
+            st['step'] = 0
+            st['exp_avg'] = m[off:off + p.numel()].view_as(p)
+            st['exp_avg_sq'] = v[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            beta1, beta2 = group['betas']
+            active = [p for p in group['params'] if p.grad is not None]
+            for p in active:
+                if p.grad.is_sparse:
+                    raise RuntimeError('RAdam does not support sparse gradients')
+                if not p.is_cuda or p.dtype != torch.float32:
+                    raise RuntimeError("hashnerf_b200 RAdam updates fp32 CUDA parameters only (no CPU fallback)")
+            # split into runs of parameters that are consecutive in memory
+            runs, cur = [], []
+            for p in active:
+                if cur and p.is_contiguous() and cur[-1].data_ptr() + cur[-1].numel() * 4 == p.data_ptr():
+                    cur.append(p)
+                else:
+                    if cur:
+                        runs.append(cur)
+                    cur = [p]
+            if cur:
+                runs.append(cur)
+            for run in runs:
+                if any(len(self.state[p]) == 0 for p in run):
+                    fresh = [p for p in run if len(self.state[p]) == 0]
+                    if len(fresh) == len(run):
+                        self._init_state(run)
+                    else:
+                        for p in fresh:
+                            self._init_state([p])
+                self._update_run(group, run, beta1, beta2)
+        return loss
+
+    def _update_run(self, group, run, beta1, beta2):
+        # fuse the longest prefixes whose grads / moments are also consecutive and whose step counts agree
+        i = 0
+        while i < len(run):
+            j = i + 1
+            st0 = self.state[run[i]]
+            while j < len(run):
+                a, b = run[j - 1], run[j]
+                sa, sb = self.state[a], self.state[b]
+                ok = (sb['step'] == st0['step']
+                      and ops._consecutive([a.grad, b.grad])
+                      and ops._consecutive([sa['exp_avg'], sb['exp_avg']])
+                      and ops._consecutive([sa['exp_avg_sq'], sb['exp_avg_sq']]))
+                if not ok:
+                    break
+                j += 1
+            span = run[i:j]
+            first = span[0]
+            for p in span:
+                st = self.state[p]
+                st['step'] += 1
+                if st['exp_avg'].dtype != torch.float32 or not st['exp_avg'].is_contiguous():
+                    st['exp_avg'] = st['exp_avg'].float().contiguous()
+                    st['exp_avg_sq'] = st['exp_avg_sq'].float().contiguous()
+            step = self.state[first]['step']
+            mode, step_size = self._rectification(step, beta1, beta2)
+            n = sum(p.numel() for p in span)
+            grad = first.grad if first.grad.is_contiguous() else None
+            if grad is None:
+                assert len(span) == 1
+                grad = first.grad.contiguous()
+            st = self.state[first]
+            with ops._on(first.device):
+                _lib.call("hn_radam_step", first.data_ptr(), grad.data_ptr(), st['exp_avg'].data_ptr(),
+                          st['exp_avg_sq'].data_ptr(), n, beta1, beta2, group['eps'], group['lr'],
+                          group['weight_decay'], step_size, mode, self.grad_scale, ops._stream())
+            i = j

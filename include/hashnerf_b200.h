@@ -1,0 +1,136 @@
+/*
+ * hashnerf_b200.h -- C ABI of libhashnerf_b200.so, the sm_100a implementation of the HashNeRF hot path
+ *                    HashEmbedder -> SHEncoder -> NeRFSmall -> raw2outputs / sample_pdf.
+ *
+ * The reference (mache102/HashNeRF-pytorch) is pure Python and has no FFI layer; the "interface each
+ * entry point replaces" is therefore the Python function whose ATen op chain it fuses.  Citations are
+ * file:line into the reference checkout.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to densely packed row-major data unless a stride is passed;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it: no allocation,
+ *     no synchronisation, no pointer retained after return (scratch is passed in by the caller);
+ *   - return value: 0 on success, a positive cudaError_t, or HN_EINVAL for a rejected argument;
+ *     hn_last_error_string() describes the last non-zero return of the calling thread;
+ *   - nothing throws, exits or prints.
+ */
+#ifndef HASHNERF_B200_H_
+#define HASHNERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HN_API __attribute__((visibility("default")))
+#else
+#define HN_API
+#endif
+
+#define HN_EINVAL (-22)
+#define HN_MAX_LEVELS 32
+#define HN_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------------------------- */
+HN_API int hn_abi_version(void);
+HN_API const char* hn_last_error_string(void);
+/* Multiprocessor count / compute capability of the current device (used to size persistent grids). */
+HN_API int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Launch-shape knobs for profiling sweeps (not part of the numerical contract): keys "hash_fwd_lpg",
+ * "hash_bwd_lpg" (levels per thread: 1,2,4,8,16; 0 = heuristic). */
+HN_API int hn_set_tuning(const char* key, int value);
+
+/* ---- (a3) spatial hash : embedding/hash_encoding.py:112-128 ------------------------------------ */
+/* hashed[i] = (XOR_d coords[i*dim+d] * prime_d) & (2^log2T - 1); dim <= 7, int64 in / int64 out as
+ * the reference; used by loss.py:29 on arbitrary integer coordinates. */
+HN_API int hn_spatial_hash(const int64_t* coords, int64_t n, int dim, int log2T, int64_t* hashed, void* stream);
+
+/* ---- (a2) voxel vertices of every level : embedding/hash_encoding.py:59-82 --------------------- */
+/* Debug/parity entry point exposing the intermediates the fused encoder never materialises:
+ * hashed [L,N,8] int64 (corner c = 4i+2j+k), vmin/vmax [L,N,3] f32 (any may be NULL).
+ * bbox = {min.x,min.y,min.z,max.x,max.y,max.z}; resolutions = floor(base*b^l) as f32 [L]. */
+HN_API int hn_voxel_vertices(const float* x, const float* bbox, const float* resolutions, int64_t N, int L,
+                      int log2T, int64_t* hashed, float* vmin, float* vmax, void* stream);
+
+/* ---- (a4-a6) multiresolution hash encoding : embedding/hash_encoding.py:84-110, 130-163 -------- */
+/* tables: [L, 2^log2T, F] f32 (level l's nn.Embedding.weight is the l-th slab).  F == 2.
+ * out: [N, L*F] f32, level-major features.  keep: [N] uint8, the mask forward() returns
+ * (last level's in-box test on the already-clamped coordinates; may be NULL). */
+HN_API int hn_hash_encode_fwd(const float* x, const float* tables, const float* bbox, const float* resolutions,
+                       int64_t N, int L, int F, int log2T, float* out, uint8_t* keep, void* stream);
+/* Autograd of the above w.r.t. the tables: dtables[l, h_c, :] += dy[p, l*F:(l+1)*F] * W_c(p) for the 8
+ * corners.  ACCUMULATES into dtables (caller zeroes).  No gradient w.r.t. x exists on this path. */
+HN_API int hn_hash_encode_bwd(const float* x, const float* dy, const float* bbox, const float* resolutions,
+                       int64_t N, int L, int F, int log2T, float* dtables, void* stream);
+
+/* ---- (a7) spherical harmonics : embedding/spherical_harmonic.py:65-103 ------------------------- */
+/* dirs [N,3] -> out [N, degree^2], 1 <= degree <= 5. */
+HN_API int hn_sh_encode(const float* dirs, int64_t N, int degree, float* out, void* stream);
+
+/* ---- (a8) NeRFSmall : models.py:151-174 as instantiated at run_nerf_helpers.py:79-84 ----------- */
+/* Geometry is fixed to the instantiated network: input_ch 32, input_ch_views 16, hidden 64,
+ * geo_feat_dim 15, 2 sigma layers, 3 colour layers, no bias.
+ * weights: the five nn.Linear.weight matrices ([out,in] row-major) packed back to back:
+ *   W0[64,32] W1[16,64] W2[64,31] W3[64,64] W4[3,64]  = 9344 floats  (HN_MLP_PARAMS).
+ * enc:   row p at enc + p*enc_stride (32 floats);   views: row (p / pts_per_view) at
+ * views + (p / pts_per_view)*views_stride (16 floats).  pts_per_view = 1 reproduces
+ * NeRFSmall.forward(x[N,48]) on a split view of x; pts_per_view = S evaluates SH once per ray
+ * (fuses run_nerf_helpers.py:219-222).  out: [N,4] = (rgb_raw[3], sigma).
+ * keep (may be NULL): sigma is written as 0 where keep[p] == 0 (run_nerf_helpers.py:225). */
+#define HN_MLP_PARAMS 9344
+HN_API int hn_mlp_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride,
+               int64_t pts_per_view, const float* weights, const uint8_t* keep, int64_t N, float* out,
+               void* stream);
+/* Backward: recomputes activations from (enc, views, weights).  dout [N,4].  d_enc [N,32] (dense, written),
+ * dweights [9344] (ACCUMULATED).  No gradient w.r.t. views on this path (directions are data).
+ * workspace: caller-provided scratch of hn_mlp_bwd_workspace_bytes(N) bytes, 16-byte aligned. */
+HN_API int64_t hn_mlp_bwd_workspace_bytes(int64_t N);
+HN_API int hn_mlp_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride,
+               int64_t pts_per_view, const float* weights, const uint8_t* keep, const float* dout, int64_t N,
+               float* d_enc, float* dweights, float* workspace, void* stream);
+
+/* ---- (a10) raw2outputs : run_nerf_helpers.py:577-628 ------------------------------------------- */
+/* raw [R,S,4], z [R,S], rays_d [R,3], noise [R,S] or NULL (already scaled by raw_noise_std).
+ * Outputs: rgb [R,3], disp [R], acc [R], weights [R,S], depth [R], entropy [R]. */
+HN_API int hn_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int64_t R,
+                     int S, int white_bkgd, float* rgb, float* disp, float* acc, float* weights, float* depth,
+                     float* entropy, void* stream);
+/* Any upstream gradient pointer may be NULL (= zero).  d_raw [R,S,4] is written. */
+HN_API int hn_composite_bwd(const float* raw, const float* z, const float* rays_d, const float* noise, int64_t R,
+                     int S, int white_bkgd, const float* d_rgb, const float* d_disp, const float* d_acc,
+                     const float* d_weights, const float* d_depth, const float* d_entropy, float* d_raw,
+                     void* stream);
+
+/* ---- (a11) sample_pdf : run_nerf_helpers.py:264-307 -------------------------------------------- */
+/* bins [R,nb], weights [R,nb-1], u [R,Ni] or NULL for det (u_i = linspace(0,1,Ni) passed as u_det [Ni]);
+ * samples [R,Ni]. */
+HN_API int hn_sample_pdf(const float* bins, const float* weights, const float* u, const float* u_det, int64_t R,
+                  int nb, int Ni, float* samples, void* stream);
+/* out[r,:] = sort(cat(a[r,:na], b[r,:nb]))  (run_nerf_helpers.py:551); na+nb <= 2048. */
+HN_API int hn_sort_concat_rows(const float* a, int na, const float* b, int nb, int64_t R, float* out, void* stream);
+
+/* ---- (a12) ray-marching set-up : run_nerf_helpers.py:514-538 ----------------------------------- */
+/* z[r,s] from near/far ([R] each, element stride nf_stride), t_vals [S] (= torch.linspace(0,1,S)),
+ * optional stratified jitter t_rand [R,S] (NULL = none). */
+HN_API int hn_coarse_z(const float* near, const float* far, int64_t nf_stride, const float* t_vals,
+                const float* t_rand, int64_t R, int S, int lindisp, float* z, void* stream);
+/* pts[r,s,:] = o[r,:] + d[r,:]*z[r,s]  (mul then add, separately rounded).  o/d rows have ray_stride. */
+HN_API int hn_ray_points(const float* rays_o, const float* rays_d, int64_t ray_stride, const float* z, int64_t R,
+                  int S, float* pts, void* stream);
+
+/* ---- section 8f "next" row 1: RAdam : radam.py:34-92 ----------------------------------------------- */
+/* One fused pass over a flat span of n parameters: moments (:58-59), weight decay (:82-83) and the
+ * rectified-Adam or degenerated-SGD update (:84-90).  step_size and the branch (`mode`: 0 = moments
+ * only, 1 = adaptive, 2 = SGD-like) are computed on the host from the step count as in :62-78.
+ * The gradient is multiplied by grad_scale first (1/world_size after a summed all-reduce). */
+HN_API int hn_radam_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
+                         float eps, float lr, float weight_decay, float step_size, int mode, float grad_scale,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HASHNERF_B200_H_ */

@@ -1,0 +1,432 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in modules) against
+ (a) golden vectors produced by the reference itself and (b) the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): hash indices / voxel vertices / encoded features bit-exact;
+floating-point outputs rel 1e-5 forward; atomically accumulated gradients rel 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import oracle as O
+from conftest import t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+FWD_RTOL, GRAD_RTOL = 1e-5, 1e-4
+
+
+def g32(a):
+    return t(np.asarray(a, dtype=np.float32)).to(DEV)
+
+
+def bit_equal(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (a.shape, b.shape, a.dtype, b.dtype)
+    if a.dtype == np.float32:
+        same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    else:
+        same = a == b
+    assert same.all(), f"{np.count_nonzero(~same)} of {same.size} elements differ"
+
+
+def close(a, b, rtol, atol=0.0, what=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True, err_msg=what)
+
+
+def make_embedder(bbox, log2T, finest=512, L=16, F=2, scale=1.0):
+    from embedding.hash_encoding import HashEmbedder
+    box = (torch.tensor(bbox[0], dtype=torch.float32), torch.tensor(bbox[1], dtype=torch.float32))
+    emb = HashEmbedder(box, n_levels=L, n_features_per_level=F, log2_hashmap_size=log2T, finest_resolution=finest)
+    tables = cases.synth_tables(L, log2T, F) * np.float32(scale)
+    with torch.no_grad():
+        for l in range(L):
+            emb.embeddings[l].weight.copy_(t(tables[l]))
+    return emb.to(DEV), tables
+
+
+def make_mlp(weights5):
+    from models import NeRFSmall
+    net = NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                    input_ch=32, input_ch_views=16)
+    with torch.no_grad():
+        for lin, w in zip(list(net.sigma_net) + list(net.color_net), weights5):
+            lin.weight.copy_(t(np.asarray(w)))
+    return net.to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------- hash
+def test_spatial_hash(golden):
+    from embedding.hash_encoding import hash
+    g = golden("hash")
+    for log2T in (4, 10, 14, 19, 22, 24):
+        bit_equal(hash(t(g["coords"]).to(DEV), log2T), g[f"h{log2T}"])
+    bit_equal(hash(t(g["coords7"]).to(DEV), 19), g["h19_dim7"])
+    # leading batch dims, like hash(voxel_indices[N,8,3]) in the reference
+    c = t(g["coords"]).to(DEV).reshape(64, 64, 3)
+    bit_equal(hash(c, 19), g["h19"].reshape(64, 64))
+
+
+@pytest.mark.parametrize("name", ["hash_encode_unit_T10", "hash_encode_odd_T10", "hash_encode_odd_T19",
+                                  "hash_encode_odd_T14_f1024"])
+def test_hash_encode_golden(golden, name):
+    g = golden(name)
+    log2T, L, finest = int(g["log2T"]), int(g["n_levels"]), int(g["finest"])
+    emb, _ = make_embedder(g["bbox"], log2T, finest=finest, L=L)
+    x = g32(g["x"])
+    hashed, vmin, vmax = emb.voxel_vertices(x)
+    bit_equal(hashed.to(torch.int32), g["hashed"])            # indices: bit-exact
+    bit_equal(vmin, g["vmin"])                                # voxel vertices: bit-exact
+    bit_equal(vmax, g["vmax"])
+    out, keep = emb(x)
+    bit_equal(out, g["out"])                                  # encoded features: bit-exact
+    bit_equal(keep, g["keep"])
+    (out * g32(g["dy"])).sum().backward()
+    dense = np.zeros((L * (1 << log2T), 2), np.float32)
+    dense[g["grad_rows"]] = g["grad_vals"]
+    got = torch.stack([e.weight.grad for e in emb.embeddings]).reshape(-1, 2)
+    close(got, dense, GRAD_RTOL, atol=1e-7, what="table gradients")
+
+
+def test_hash_encode_single_level_keep_mask(golden):
+    g = golden("hash_encode_L1")
+    emb, _ = make_embedder(g["bbox"], 10, L=1)
+    out, keep = emb(g32(g["x"]))
+    bit_equal(out, g["out"])
+    bit_equal(keep, g["keep"])
+    assert not bool(keep.all()) and bool(keep.any())
+
+
+@pytest.mark.parametrize("log2T,bbox,n", [(14, cases.BBOX_ODD, 40_000), (19, cases.BBOX_UNIT, 40_000),
+                                           (19, cases.BBOX_ODD, 33_333), (22, cases.BBOX_ODD, 8_191)])
+def test_hash_encode_vs_oracle(log2T, bbox, n):
+    emb, tables = make_embedder(bbox, log2T)
+    x = cases.points_in_box(n, bbox, seed=1000 + log2T)
+    lo, hi = t(np.float32(bbox[0])), t(np.float32(bbox[1]))
+    want, want_keep = O.hash_encode(t(x), t(tables), lo, hi, O.level_resolutions(), log2T)
+    out, keep = emb(g32(x))
+    bit_equal(out, want)
+    bit_equal(keep, want_keep)
+    dy = np.random.RandomState(5).randn(n, 32).astype(np.float32)
+    (out * g32(dy)).sum().backward()
+    an = O.hash_encode_grad_tables(t(x), t(dy), lo, hi, O.level_resolutions(), log2T, 2)
+    got = torch.stack([e.weight.grad for e in emb.embeddings]).double().cpu()
+    scale = an.abs().max().item()
+    assert (got - an).abs().max().item() <= GRAD_RTOL * scale
+
+
+@pytest.mark.parametrize("lpg", [1, 2, 4, 8, 16])
+def test_hash_encode_launch_shapes_agree(lpg):
+    from hn_b200 import _lib
+    emb, tables = make_embedder(cases.BBOX_ODD, 12)
+    x = g32(cases.points_in_box(5000, cases.BBOX_ODD, 77))
+    ref_out, _ = emb(x)
+    _lib.set_tuning("hash_fwd_lpg", lpg)
+    _lib.set_tuning("hash_bwd_lpg", lpg)
+    try:
+        out, _ = emb(x)
+        bit_equal(out, ref_out)
+        dy = torch.randn_like(out)
+        (out * dy).sum().backward()
+        g1 = torch.stack([e.weight.grad for e in emb.embeddings]).clone()
+    finally:
+        _lib.set_tuning("hash_fwd_lpg", 0)
+        _lib.set_tuning("hash_bwd_lpg", 0)
+    for e in emb.embeddings:
+        e.weight.grad = None
+    out2, _ = emb(x)
+    (out2 * dy).sum().backward()
+    g2 = torch.stack([e.weight.grad for e in emb.embeddings])
+    close(g1, g2, GRAD_RTOL, atol=1e-6 * g2.abs().max().item())
+
+
+@pytest.mark.parametrize("n", [0, 1, 255, 257])
+def test_hash_encode_ragged_and_empty(n):
+    emb, tables = make_embedder(cases.BBOX_ODD, 10)
+    x = cases.points_in_box(max(n, 16), cases.BBOX_ODD, 9)[:n]
+    out, keep = emb(g32(x).reshape(n, 3))
+    assert out.shape == (n, 32) and keep.shape == (n,)
+    if n:
+        want, _ = O.hash_encode(t(x), t(tables), t(np.float32(cases.BBOX_ODD[0])), t(np.float32(cases.BBOX_ODD[1])),
+                                O.level_resolutions(), 10)
+        bit_equal(out, want)
+
+
+@pytest.mark.parametrize("F,L", [(4, 8), (1, 5), (2, 3)])
+def test_hash_encode_other_feature_widths(F, L):
+    emb, tables = make_embedder(cases.BBOX_UNIT, 11, L=L, F=F)
+    x = cases.points_in_box(3000, cases.BBOX_UNIT, 31)
+    res = O.level_resolutions(16, 512, L)
+    want, _ = O.hash_encode(t(x), t(tables), t(np.float32(cases.BBOX_UNIT[0])), t(np.float32(cases.BBOX_UNIT[1])),
+                            res, 11)
+    out, _ = emb(g32(x))
+    bit_equal(out, want)
+    dy = np.random.RandomState(6).randn(3000, L * F).astype(np.float32)
+    (out * g32(dy)).sum().backward()
+    an = O.hash_encode_grad_tables(t(x), t(dy), t(np.float32(cases.BBOX_UNIT[0])), t(np.float32(cases.BBOX_UNIT[1])),
+                                   res, 11, F)
+    got = torch.stack([e.weight.grad for e in emb.embeddings]).double().cpu()
+    assert (got - an).abs().max().item() <= GRAD_RTOL * an.abs().max().item()
+
+
+def test_hash_encode_full_size_properties():
+    """BASELINE config 2 size (2^24 points, T=19): properties that need no full-size oracle."""
+    n, log2T = 1 << 24, 19
+    emb, tables = make_embedder(cases.BBOX_UNIT, log2T)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.rand(n, 3, device=DEV, generator=gen) * 3.0 - 1.5
+    out, keep = emb(x)
+    assert bool(keep.all())
+    # (1) a random subset agrees bit-for-bit with the oracle
+    idx = torch.randint(0, n, (4096,), device=DEV, generator=gen)
+    want, _ = O.hash_encode(x[idx].cpu(), t(tables), t(np.float32(cases.BBOX_UNIT[0])),
+                            t(np.float32(cases.BBOX_UNIT[1])), O.level_resolutions(), log2T)
+    bit_equal(out[idx], want)
+    # (2) linearity in the tables: scaling by a power of two scales every rounding step exactly
+    with torch.no_grad():
+        for e in emb.embeddings:
+            e.weight.mul_(4.0)
+    out4, _ = emb(x)
+    bit_equal(out4.detach(), (out.detach() * 4.0))
+    # (3) backward conserves mass: corner weights sum to 1, so sum(dtable[l]) == sum(dy[:, l])
+    dy = torch.ones(n, 32, device=DEV)
+    for e in emb.embeddings:
+        e.weight.grad = None
+    out4.backward(dy)
+    sums = torch.stack([e.weight.grad.double().sum() for e in emb.embeddings]).cpu().numpy()
+    np.testing.assert_allclose(sums, np.full(16, 2.0 * n), rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- SH
+def test_sh_golden(golden):
+    from embedding.spherical_harmonic import SHEncoder
+    g = golden("sh")
+    for deg in (1, 2, 3, 4, 5):
+        bit_equal(SHEncoder(degree=deg)(g32(g["dirs"])), g[f"deg{deg}"])
+    out = SHEncoder()(g32(g["dirs"]).reshape(16, 32, 3))
+    assert out.shape == (16, 32, 16)
+
+
+# ---------------------------------------------------------------------------------------------- MLP
+def test_mlp_golden(golden):
+    g = golden("mlp")
+    net = make_mlp([g[f"w{i}"] for i in range(5)])
+    x = g32(g["x"]).requires_grad_(True)
+    out = net(x)
+    close(out, g["out"], FWD_RTOL, atol=1e-6, what="mlp forward")
+    (out * g32(g["dout"])).sum().backward()
+    ws = list(net.sigma_net) + list(net.color_net)
+    close(x.grad[:, :32], g["dx"][:, :32], GRAD_RTOL, atol=1e-5, what="d_enc")
+    for i in range(5):
+        close(ws[i].weight.grad, g[f"dw{i}"], GRAD_RTOL, atol=2e-5 * np.abs(g[f"dw{i}"]).max(), what=f"dW{i}")
+
+
+@pytest.mark.parametrize("n,per_ray", [(1, 1), (127, 1), (129, 1), (64 * 50, 64), (192 * 7, 192)])
+def test_mlp_vs_oracle(n, per_ray):
+    sig, col = cases.mlp_weights(70 + n % 7)
+    net = make_mlp(sig + col)
+    rs = np.random.RandomState(n)
+    enc = (rs.randn(n, 32) * 0.3).astype(np.float32)
+    views = rs.randn(n // per_ray, 16).astype(np.float32)
+    keep = rs.rand(n) > 0.1
+    dout = rs.randn(n, 4).astype(np.float32)
+    # oracle
+    ws = [t(w).requires_grad_(True) for w in sig + col]
+    e_t = t(enc).requires_grad_(True)
+    full = torch.cat([e_t, t(views).repeat_interleave(per_ray, 0)], -1)
+    o = O.nerf_small(full, ws[:2], ws[2:])
+    o = torch.cat([o[:, :3], torch.where(t(keep), o[:, 3], torch.zeros(()))[:, None]], -1)
+    (o * t(dout)).sum().backward()
+    # CUDA
+    e_g = g32(enc).requires_grad_(True)
+    out = net.forward_fused(e_g, g32(views), per_ray, t(keep).to(DEV))
+    close(out, o, FWD_RTOL, atol=1e-6)
+    (out * g32(dout)).sum().backward()
+    close(e_g.grad, e_t.grad, GRAD_RTOL, atol=1e-5)
+    for w_o, lin in zip(ws, list(net.sigma_net) + list(net.color_net)):
+        close(lin.weight.grad, w_o.grad, GRAD_RTOL, atol=2e-5 * w_o.grad.abs().max().item())
+
+
+# ---------------------------------------------------------------------------------------------- compositing
+@pytest.mark.parametrize("tag,white", [("black", False), ("white", True)])
+def test_composite_golden(golden, tag, white):
+    from run_nerf_helpers import raw2outputs
+    g = golden("composite")
+    raw = g32(g["raw"]).requires_grad_(True)
+    rgb, disp, acc, wts, depth, ent = raw2outputs(raw, g32(g["z"]), g32(g["rays_d"]), 0, white)
+    for name, val, atol in (("rgb", rgb, 1e-6), ("acc", acc, 1e-6), ("weights", wts, 1e-7), ("depth", depth, 1e-5),
+                            ("disp", disp, 1e-6), ("entropy", ent, 2e-6)):
+        close(val, g[f"{tag}_{name}"], FWD_RTOL, atol=atol, what=name)
+    assert torch.isnan(depth[0])                       # sum(w) == 0 -> NaN depth, like the reference
+    good = torch.ones(raw.shape[0], dtype=torch.bool, device=DEV)
+    good[0] = False
+    good[2] = False
+    wm = g32(g["w_misc"])
+    loss = (rgb * g32(g["w_rgb"]))[good].sum() + (acc * wm[:, 0])[good].sum() + (depth * wm[:, 1])[good].sum() \
+        + (ent * wm[:, 2])[good].sum() + (wts * g32(g["w_wts"]))[good].sum()
+    loss.backward()
+    want = g[f"{tag}_draw"]
+    close(raw.grad, want, GRAD_RTOL, atol=2e-5 * np.abs(want[np.isfinite(want)]).max(), what="d_raw")
+
+
+def test_composite_noise_and_disp_grad(golden):
+    g = golden("composite")
+    from hn_b200 import ops
+    raw_c = t(g["raw"])[4:].clone().requires_grad_(True)       # rows with sum(w) > 0 only
+    z, d, noise = t(g["z"])[4:], t(g["rays_d"])[4:], t(g["noise"])[4:]
+    o = O.composite(raw_c, z, d, noise, True)
+    w = [torch.randn(v.shape, generator=torch.Generator().manual_seed(i)) for i, v in enumerate(o)]
+    sum((a * b).sum() for a, b in zip(o, w)).backward()
+    raw_g = raw_c.detach().to(DEV).requires_grad_(True)
+    got = ops.CompositeFn.apply(raw_g, z.to(DEV), d.to(DEV), noise.to(DEV), True)
+    for a, b in zip(got, o):
+        close(a, b, FWD_RTOL, atol=2e-6)
+    sum((a * b.to(DEV)).sum() for a, b in zip(got, w)).backward()
+    close(raw_g.grad, raw_c.grad, GRAD_RTOL, atol=2e-5 * raw_c.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("S", [1, 2, 31, 33, 64, 192, 257])
+def test_composite_sample_counts(S):
+    from hn_b200 import ops
+    rs = np.random.RandomState(S)
+    R = 37
+    raw = rs.randn(R, S, 4).astype(np.float32)
+    raw[..., 3] = raw[..., 3] * 2 + 1
+    z = np.sort(2 + 4 * rs.rand(R, S).astype(np.float32), -1)
+    d = rs.randn(R, 3).astype(np.float32)
+    want = O.composite(t(raw), t(z), t(d), None, False)
+    got = ops.CompositeFn.apply(g32(raw), g32(z), g32(d), None, False)
+    for a, b in zip(got, want):
+        close(a, b, FWD_RTOL, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------- sampling
+def test_sample_pdf_golden(golden):
+    from hn_b200 import ops
+    g = golden("sample_pdf")
+    got = ops.sample_pdf(g32(g["bins"]), g32(g["weights"]), g["u"].shape[1], u=g32(g["u"]))
+    close(got, g["samples_rand"], FWD_RTOL, atol=2e-5, what="random u")
+    from run_nerf_helpers import sample_pdf
+    got = sample_pdf(g32(g["bins"]), g32(g["weights"]), g["u"].shape[1], det=True)
+    close(got, g["samples_det"], FWD_RTOL, atol=2e-5, what="det")
+
+
+def test_sort_concat_rows():
+    from hn_b200 import ops
+    for na, nb, R in [(64, 128, 100), (1, 1, 3), (5, 0, 4), (24, 40, 48), (700, 1300, 5), (64, 64, 1000)]:
+        gen = torch.Generator(device=DEV).manual_seed(na + nb)
+        a = torch.rand(R, na, device=DEV, generator=gen).sort(-1).values
+        b = torch.rand(R, nb, device=DEV, generator=gen)
+        if na > 3 and nb > 3:
+            b[:, 0] = a[:, 2]  # duplicates
+        want = torch.sort(torch.cat([a, b], -1), -1).values
+        bit_equal(ops.sort_concat_rows(a, b), want)
+
+
+@pytest.mark.parametrize("lindisp,perturb", [(False, False), (False, True), (True, True)])
+def test_coarse_z_and_points_bit_exact(lindisp, perturb):
+    from hn_b200 import ops
+    R, S = 77, 64
+    rays = cases.rays(R, 5)
+    rays[:, 6] = 0.5 + np.random.RandomState(1).rand(R).astype(np.float32)
+    t_rand = np.random.RandomState(2).rand(R, S).astype(np.float32) if perturb else None
+    rb = g32(rays)
+    tv = torch.linspace(0., 1., steps=S, device=DEV)
+    bit_equal(tv, torch.linspace(0., 1., steps=S))
+    z = ops.coarse_z(rb[:, 6], rb[:, 7], 11, tv, None if t_rand is None else g32(t_rand), R, S, lindisp)
+    want = O.coarse_z(t(rays[:, 6:7]), t(rays[:, 7:8]), S, lindisp, None if t_rand is None else t(t_rand))
+    bit_equal(z, want.contiguous())
+    pts = ops.ray_points(rb[:, 0:3], rb[:, 3:6], 11, z)
+    want_pts = t(rays[:, None, 0:3]) + t(rays[:, None, 3:6]) * want[:, :, None]
+    bit_equal(pts, want_pts)
+
+
+# ---------------------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("name", ["render_rays_perturb", "render_rays_det_noise"])
+def test_render_rays_golden(golden, name):
+    from embedding.spherical_harmonic import SHEncoder
+    from run_nerf_helpers import render_rays, run_network
+    g = golden(name)
+    emb, _ = make_embedder(g["bbox"], int(g["log2T"]), scale=float(g["table_scale"]))
+    coarse = make_mlp([g[f"coarse_w{i}"] for i in range(5)])
+    fine = make_mlp([g[f"fine_w{i}"] for i in range(5)])
+    sh = SHEncoder()
+    qfn = lambda inputs, viewdirs, fn: run_network(inputs, viewdirs, fn, embed_fn=emb, embeddirs_fn=sh)
+    ret = render_rays(g32(g["rays"]), coarse, qfn, int(g["N_samples"]), embed_fn=emb, retraw=True,
+                      perturb=float(g["perturb"]), N_importance=int(g["N_importance"]), network_fine=fine,
+                      white_bkgd=bool(g["white_bkgd"]), raw_noise_std=float(g["raw_noise_std"]), pytest=True)
+    for k in ("rgb0", "depth0", "acc0", "sparsity_loss0", "rgb_map", "depth_map", "acc_map", "sparsity_loss",
+              "z_std", "raw"):
+        want = g["ret_" + k]
+        close(ret[k], want, 5e-5, atol=2e-5 * max(1.0, float(np.abs(want).max())), what=k)
+    tgt = g32(g["target"])
+    loss = ((ret["rgb_map"] - tgt) ** 2).mean() + ((ret["rgb0"] - tgt) ** 2).mean() \
+        + 1e-3 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum())
+    close(loss, g["loss"], 2e-5)
+    loss.backward()
+    gt = torch.stack([e.weight.grad for e in emb.embeddings])
+    want = g["grad_tables"]
+    close(gt, want, 1e-3, atol=2e-4 * np.abs(want).max(), what="table grads")
+    for tag, net in (("coarse", coarse), ("fine", fine)):
+        for i, lin in enumerate(list(net.sigma_net) + list(net.color_net)):
+            want = g[f"{tag}_dw{i}"]
+            close(lin.weight.grad, want, 1e-3, atol=2e-4 * np.abs(want).max(), what=f"{tag} dW{i}")
+
+
+# ---------------------------------------------------------------------------------------------- next rows
+def test_radam_golden(golden):
+    from radam import RAdam
+    g = golden("radam")
+    buf = torch.zeros(257 * 3 + 64 * 2, device=DEV)
+    p = torch.nn.Parameter(g32(g["p0"]))
+    q = torch.nn.Parameter(g32(g["q0"]))
+    opt = RAdam([{"params": [p], "weight_decay": 1e-6}, {"params": [q], "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+    for step in range(g["grads_p"].shape[0]):
+        p.grad = g32(g["grads_p"][step])
+        q.grad = g32(g["grads_q"][step])
+        opt.step()
+        for grp in opt.param_groups:
+            grp["lr"] = 0.01 * (0.1 ** ((step + 1) / 10000.0))
+        close(p, g["traj_p"][step], 2e-6, atol=1e-8, what=f"p step {step}")
+        close(q, g["traj_q"][step], 2e-6, atol=1e-10, what=f"q step {step}")
+    assert set(opt.state[p].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_tv_loss_golden(golden):
+    from loss import total_variation_loss
+    g = golden("tv_loss")
+    emb, tables = make_embedder(cases.BBOX_UNIT, 12)
+    real = torch.randint
+    for level in (0, 3, 7, 15):
+        torch.randint = lambda *a, **k: t(g[f"l{level}_min_vertex"]).clone()
+        try:
+            tv = total_variation_loss(emb.embeddings[level], emb.base_resolution, emb.finest_resolution, level, 12,
+                                      n_levels=16)
+        finally:
+            torch.randint = real
+        close(tv, g[f"l{level}_tv"], 2e-5)
+        emb.embeddings[level].weight.grad = None
+        tv.backward()
+        dense = np.zeros((1 << 12, 2), np.float32)
+        dense[g[f"l{level}_grad_rows"]] = g[f"l{level}_grad_vals"]
+        close(emb.embeddings[level].weight.grad, dense, GRAD_RTOL, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------- errors
+def test_error_behaviour():
+    from embedding.hash_encoding import HashEmbedder, hash
+    from hn_b200 import _lib
+    emb, _ = make_embedder(cases.BBOX_UNIT, 10)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        emb(torch.rand(4, 3))
+    with pytest.raises(RuntimeError, match="dim must be in"):
+        hash(torch.zeros(3, 8, dtype=torch.int64, device=DEV), 19)
+    with pytest.raises(RuntimeError):
+        _lib.set_tuning("no_such_knob", 1)
+    with pytest.raises(NotImplementedError):
+        from models import NeRFSmall
+        NeRFSmall()  # the reference's never-used default geometry
