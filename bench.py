@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- hash-encode fwd+bwd throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 2^24 uniform points in the bbox per GPU, L=16, F=2,
+log2_hashmap_size=19, finest_res=512; one step = forward gather + zero-grad + backward scatter (+ one NCCL
+all-reduce of the 64 MiB table gradient when N > 1: the data-parallel exchange step the north star names).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "hashnerf-pytorch_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BYTES_PER_SAMPLE_FWD = 12 + 16 * (8 * 2 * 4 + 2 * 4)   # 1164
+BYTES_PER_SAMPLE_BWD = 12 + 16 * (2 * 4 + 8 * 2 * 4)   # 1164
+BBOX = ((-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))
+METRIC = "hash_encode_fwd_bwd_msamples_per_s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def time_loop(fn, steps, warmup, dist=None):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's PyTorch encoder on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_hash_encode_fwd_bwd(n_points: int, log2T: int, steps: int, warmup: int):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    lo, hi = torch.tensor(BBOX[0]), torch.tensor(BBOX[1])
+    x = torch.rand(n_points, 3, generator=g) * (hi - lo) + lo
+    dy = torch.randn(n_points, 32, generator=g)
+    tables = ((torch.rand(16, 1 << log2T, 2, generator=g) * 2e-4) - 1e-4).requires_grad_(True)
+    res = O.level_resolutions()
+
+    def step():
+        tables.grad = None
+        out, _ = O.hash_encode(x, tables, lo, hi, res, log2T)
+        out.backward(dy)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n_points / dt / 1e6, dt * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 1 << 16
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    v, ms, cores = cpu_hash_encode_fwd_bwd(n, args.log2T, steps, warmup)
+    sample = f"{n} of the 2^24 points per step (oracle port of hash_encoding.py fwd + autograd bwd, torch CPU fp32)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n),
+        "cpu_baseline": {"value": round(v, 4), "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, n_points):
+    return {"workload": f"cfg2 hash-encode fwd+bwd: 2^{int(np.log2(args.points))} uniform points in bbox per GPU, L=16, "
+                        f"F=2, log2_hashmap_size={args.log2T}, base 16, finest 512",
+            "points_per_step_per_gpu": n_points, "log2_hashmap_size": args.log2T,
+            "l2": "inputs larger than L2 (x 201 MB + dY 2.1 GB + features 2.1 GB per step); the 64 MiB table stays "
+                  "L2-resident across steps, as in steady-state training",
+            "parallelism": f"dp{args.gpus} (points sharded, table gradient all-reduced)" if args.gpus > 1 else "single"}
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+def train_step_extra(dev, n_rand, steps=8, warmup=3):
+    """BASELINE configs[2]/[3] shape: full coarse+fine render + loss + backward + RAdam on synthetic rays."""
+    from embedding.hash_encoding import HashEmbedder
+    from embedding.spherical_harmonic import SHEncoder
+    from models import NeRFSmall
+    from radam import RAdam
+    from run_nerf_helpers import render_rays, run_network, img2mse
+    torch.manual_seed(0)
+    emb = HashEmbedder((torch.tensor(BBOX[0]), torch.tensor(BBOX[1])), log2_hashmap_size=19).to(dev)
+    mk = lambda: NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                           input_ch=32, input_ch_views=16).to(dev)
+    coarse, fine, sh = mk(), mk(), SHEncoder()
+    opt = RAdam([{"params": list(coarse.parameters()) + list(fine.parameters()), "weight_decay": 1e-6},
+                 {"params": list(emb.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+    g = torch.Generator(device=dev).manual_seed(1)
+    o = torch.tensor([0., 0., 4.], device=dev) + 0.1 * torch.randn(n_rand, 3, device=dev, generator=g)
+    d = -o / o.norm(dim=-1, keepdim=True) + 0.2 * torch.randn(n_rand, 3, device=dev, generator=g)
+    rays = torch.cat([o, d, torch.full((n_rand, 1), 2., device=dev), torch.full((n_rand, 1), 6., device=dev),
+                      d / d.norm(dim=-1, keepdim=True)], -1)
+    target = torch.rand(n_rand, 3, device=dev, generator=g)
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+
+    def step():
+        ret = render_rays(rays, coarse, qfn, 64, embed_fn=emb, retraw=True, perturb=1., N_importance=128,
+                          network_fine=fine, white_bkgd=True)
+        opt.zero_grad()
+        loss = img2mse(ret["rgb_map"], target) + img2mse(ret["rgb0"], target) \
+            + 1e-10 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum())
+        loss.backward()
+        opt.step()
+
+    ms = time_loop(step, steps, warmup) / steps
+    return n_rand / ms * 1e3, ms
+
+
+def run_ours(args):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    from hn_b200 import _lib, ops
+    from embedding.hash_encoding import HashEmbedder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    n, log2T, L, F = args.points, args.log2T, 16, 2
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    lo, hi = torch.tensor(BBOX[0], device=dev), torch.tensor(BBOX[1], device=dev)
+    x = torch.rand(n, 3, device=dev, generator=gen) * (hi - lo) + lo
+    dy = torch.randn(n, L * F, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    torch.manual_seed(0)  # identical tables on every rank
+    emb = HashEmbedder((lo.cpu(), hi.cpu()), log2_hashmap_size=log2T).to(dev)
+    tables = emb.flat_tables()
+    box, res = emb._geometry(dev)
+    dflat = torch.zeros(tables.numel(), device=dev)
+    out_holder = {}
+
+    def fwd():
+        out_holder["y"] = ops.hash_encode_forward(x, tables, box, res, L, F, log2T, want_keep=True)[0]
+
+    def bwd():
+        ops.hash_encode_backward(x, dy, box, res, L, F, log2T, dflat)
+
+    def step():
+        dflat.zero_()
+        fwd()
+        bwd()
+        if dist is not None:
+            dist.all_reduce(dflat)
+
+    # ---- headline: device-resident inputs
+    clocks = ClockSampler(local)
+    launches0 = _lib.launches
+    if rank == 0:
+        clocks.start()
+    total_ms = time_loop(step, args.steps, args.warmup, dist)
+    clock_report = clocks.stop() if rank == 0 else None
+    gpu_launches = (_lib.launches - launches0) * args.steps // (args.steps + args.warmup)
+    ms_per_step = total_ms / args.steps
+    value = world * n / ms_per_step / 1e3  # Msamples/s, whole job
+
+    # ---- per-kernel timing for the roofline (same stream, CUDA events)
+    fwd_ms = time_loop(fwd, args.steps, 2) / args.steps
+    bwd_ms = time_loop(bwd, args.steps, 2) / args.steps
+    peak, peak_src = peaks()
+    dom = "hash_bwd_kernel" if bwd_ms >= fwd_ms else "hash_fwd_kernel"
+    dom_ms = max(bwd_ms, fwd_ms)
+    dom_bytes = n * (BYTES_PER_SAMPLE_BWD if dom == "hash_bwd_kernel" else BYTES_PER_SAMPLE_FWD)
+    achieved = dom_bytes / dom_ms / 1e6  # GB/s
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": round(dom_ms, 4),
+                "fwd": {"ms": round(fwd_ms, 4), "gbs": round(n * BYTES_PER_SAMPLE_FWD / fwd_ms / 1e6, 1)},
+                "bwd": {"ms": round(bwd_ms, 4), "gbs": round(n * BYTES_PER_SAMPLE_BWD / bwd_ms / 1e6, 1)},
+                "fwd_bwd_frac_of_hbm": round(n * (BYTES_PER_SAMPLE_FWD + BYTES_PER_SAMPLE_BWD)
+                                             / (fwd_ms + bwd_ms) / 1e6 / peak, 4)}
+
+    # ---- end to end through the public API with host inputs
+    x_host = x.cpu().pin_memory()
+    x_dev = torch.empty_like(x)
+    result_host = torch.empty(L, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        x_dev.copy_(x_host, non_blocking=True)                   # H2D of the step's input points
+        for e in emb.embeddings:
+            e.weight.grad = None
+        feats, _keep = emb(x_dev)                                # HashEmbedder.forward (public API)
+        feats.backward(dy)                                       # autograd -> scatter kernel
+        g = torch.stack([e.weight.grad.sum() for e in emb.embeddings])
+        if dist is not None:
+            dist.all_reduce(g)
+        result_host.copy_(g, non_blocking=True)                  # D2H of the step's result (per-level grad sums)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms = time_loop(e2e_step, e2e_steps, 2, dist) / e2e_steps
+    e2e = {"value": round(world * n / e2e_ms / 1e3, 2), "unit": "Msamples/s", "h2d_bytes_per_step": n * 12,
+           "d2h_bytes_per_step": L * 4, "ms_per_step": round(e2e_ms, 3),
+           "api": "HashEmbedder.forward + autograd backward; points from pinned host memory each step, upstream "
+                  "gradient dY resident (stands for the downstream MLP), per-level gradient sums read back"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- extras (rank 0 only, N=1 only): other table sizes, training step
+    extra = {}
+    if world == 1 and not args.no_extra:
+        del x_host, x_dev
+        for t_log2 in (14, 22):
+            e2 = HashEmbedder((lo.cpu(), hi.cpu()), log2_hashmap_size=t_log2).to(dev)
+            tb, (bx, rs) = e2.flat_tables(), e2._geometry(dev)
+            dg = torch.zeros(tb.numel(), device=dev)
+
+            def s2():
+                dg.zero_()
+                ops.hash_encode_forward(x, tb, bx, rs, L, F, t_log2, want_keep=True)
+                ops.hash_encode_backward(x, dy, bx, rs, L, F, t_log2, dg)
+            m = time_loop(s2, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+            extra[f"msamples_per_s_T{t_log2}"] = round(n / m / 1e3, 1)
+            del e2, tb, dg
+        del dy, out_holder["y"]
+        torch.cuda.empty_cache()
+        for n_rand in (1024, 8192):
+            rps, ms = train_step_extra(dev, n_rand)
+            extra[f"train_rays_per_s_nrand{n_rand}"] = round(rps, 1)
+            extra[f"train_ms_per_step_nrand{n_rand}"] = round(ms, 3)
+        extra["train_step"] = "render_rays 64+128 samples/ray, perturb=1, white_bkgd, mse+sparsity, backward, RAdam (no TV)"
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = 1 << 17
+        v, ms, cores = cpu_hash_encode_fwd_bwd(n_cpu, log2T, steps=2, warmup=1)
+        cpu = {"value": round(v, 4), "unit": "Msamples/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} of the 2^24 points, 2 timed passes after 1 warm-up ({ms:.0f} ms/pass), oracle port "
+                         "of the reference's PyTorch encoder fwd + autograd bwd"}
+
+    line = {"metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
+            "clocks": clock_report, "extra": extra}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2T", type=int, default=19)
+    ap.add_argument("--points", type=int, default=1 << 24)
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

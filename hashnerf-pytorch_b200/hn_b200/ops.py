@@ -67,10 +67,13 @@ class _on:
 
 
 def _consecutive(tensors: Sequence[torch.Tensor]) -> bool:
-    """True if the (contiguous, fp32) tensors sit back to back in one allocation."""
+    """True if the (contiguous, fp32) tensors sit back to back in ONE storage (adjacent addresses of
+    separate allocations do not count: a view spanning them would leave its storage)."""
     addr = tensors[0].data_ptr()
+    base = tensors[0].untyped_storage().data_ptr()
     for t in tensors:
-        if t.dtype != torch.float32 or not t.is_contiguous() or t.data_ptr() != addr:
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.data_ptr() != addr \
+                or t.untyped_storage().data_ptr() != base:
             return False
         addr += t.numel() * 4
     return True

@@ -75,7 +75,7 @@ class RAdam(Optimizer):
             # split into runs of parameters that are consecutive in memory
             runs, cur = [], []
             for p in active:
-                if cur and p.is_contiguous() and cur[-1].data_ptr() + cur[-1].numel() * 4 == p.data_ptr():
+                if cur and ops._consecutive([cur[-1], p]):
                     cur.append(p)
                 else:
                     if cur:
