@@ -411,7 +411,7 @@ def test_radam_golden(golden):
         for grp in opt.param_groups:
             grp["lr"] = 0.01 * (0.1 ** ((step + 1) / 10000.0))
         close(p, g["traj_p"][step], 1e-5, atol=1e-8, what=f"p step {step}")
-        close(q, g["traj_q"][step], 1e-5, atol=1e-10, what=f"q step {step}")
+        close(q, g["traj_q"][step], 1e-5, atol=2e-9, what=f"q step {step}")
     assert set(opt.state[p].keys()) == {"step", "exp_avg", "exp_avg_sq"}
 
 
