@@ -67,6 +67,9 @@ class HashEmbedder(nn.Module):
             nn.init.uniform_(emb.weight, a=-0.0001, b=0.0001)
         self._flatten_parameters()
         self._geom_cache = {}
+        # None: re-order large batches by grid cell before encoding (results unchanged, see ops.HashEncodeFn);
+        # True / False force the choice.
+        self.coherent = None
 
     # -- storage --------------------------------------------------------------------------------
     def _level_weights(self):
@@ -122,7 +125,7 @@ class HashEmbedder(nn.Module):
         box, res = self._geometry(pts.device)
         self._flatten_parameters()
         feats, keep = ops.HashEncodeFn.apply(pts, box, res, self.log2_hashmap_size, self.n_features_per_level,
-                                             *self._level_weights())
+                                             self.coherent, *self._level_weights())
         if len(lead) != 1:
             feats, keep = feats.reshape(*lead, self.out_dim), keep.reshape(lead)
         return feats, keep

@@ -138,21 +138,76 @@ def hash_encode_backward(x, dy, bbox6, resolutions, L, F, log2T, dtables_flat):
                   x.shape[0], L, F, log2T, dtables_flat.data_ptr(), _stream())
 
 
+def hash_sort_points(x, bbox6, grid_res: int = 128) -> torch.Tensor:
+    """Counting sort of the points by grid cell -> xs4 [N,4] = (x, y, z, bit-cast original row)."""
+    dev = _need_cuda(x, bbox6)
+    x = _f32c(x)
+    N = x.shape[0]
+    lib = _lib.load()
+    nbytes = lib.hn_hash_sort_workspace_bytes(N, int(grid_res))
+    if nbytes < 0:
+        raise RuntimeError("hn_hash_sort_workspace_bytes rejected its arguments")
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=dev)
+    xs4 = torch.empty(N, 4, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_hash_sort_points", x.data_ptr(), bbox6.data_ptr(), N, int(grid_res), ws.data_ptr(),
+                  xs4.data_ptr(), _stream())
+    return xs4
+
+
+def hash_encode_forward_sorted(xs4, tables_flat, bbox6, resolutions, L, F, log2T, want_keep=True):
+    dev = _need_cuda(xs4, tables_flat, bbox6, resolutions)
+    N = xs4.shape[0]
+    out = torch.empty(N, L * F, dtype=torch.float32, device=dev)
+    keep = torch.empty(N, dtype=torch.uint8, device=dev) if want_keep else None
+    with _on(dev):
+        _lib.call("hn_hash_encode_fwd_sorted", xs4.data_ptr(), tables_flat.data_ptr(), bbox6.data_ptr(),
+                  resolutions.data_ptr(), N, L, F, log2T, out.data_ptr(), _ptr(keep), _stream())
+    return out, keep
+
+
+def hash_encode_backward_sorted(xs4, dy, bbox6, resolutions, L, F, log2T, dtables_flat):
+    dev = _need_cuda(xs4, dy, bbox6, resolutions, dtables_flat)
+    dy = _f32c(dy)
+    with _on(dev):
+        _lib.call("hn_hash_encode_bwd_sorted", xs4.data_ptr(), dy.data_ptr(), bbox6.data_ptr(),
+                  resolutions.data_ptr(), xs4.shape[0], L, F, log2T, dtables_flat.data_ptr(), _stream())
+
+
+# Points are re-ordered by grid cell before encoding when there are at least this many of them (the sort
+# costs a few passes over the points; below this size the launch overhead outweighs the coherence gain).
+SORT_MIN_POINTS = 1 << 20
+
+
+def sort_grid_res(n_points: int) -> int:
+    """About one point per cell (measured optimum at 2^24 points: 256^3 cells), capped so that the
+    counter array stays small next to the points."""
+    return int(min(256, max(16, round(n_points ** (1.0 / 3.0)))))
+
+
 class HashEncodeFn(torch.autograd.Function):
-    """features, keep = HashEncodeFn.apply(x, bbox6, resolutions, log2T, F, *level_tables)
+    """features, keep = HashEncodeFn.apply(x, bbox6, resolutions, log2T, F, coherent, *level_tables)
 
     ``level_tables`` are the L ``nn.Embedding.weight`` parameters ([2^T, F] each).  Autograd routes the
     table gradient to each of them; the gradients returned are slices of ONE flat buffer filled by a
     single scatter kernel (the reference produces 16 separate dense gradients through
-    embedding_dense_backward, hash_encoding.py:106)."""
+    embedding_dense_backward, hash_encoding.py:106).  ``coherent``: None = sort the points by grid cell when
+    there are many of them, True / False = force."""
 
     @staticmethod
-    def forward(ctx, x, bbox6, resolutions, log2T, F, *level_tables):
+    def forward(ctx, x, bbox6, resolutions, log2T, F, coherent, *level_tables):
         L = len(level_tables)
         flat = pack(level_tables)
-        out, keep = hash_encode_forward(x, flat, bbox6, resolutions, L, F, log2T)
-        ctx.save_for_backward(x, bbox6, resolutions)
-        ctx.meta = (L, F, log2T)
+        N = x.shape[0]
+        use_sort = (N >= SORT_MIN_POINTS) if coherent is None else (bool(coherent) and N > 0)
+        if use_sort:
+            xs4 = hash_sort_points(x, bbox6, sort_grid_res(N))
+            out, keep = hash_encode_forward_sorted(xs4, flat, bbox6, resolutions, L, F, log2T)
+            ctx.save_for_backward(xs4, bbox6, resolutions)
+        else:
+            out, keep = hash_encode_forward(x, flat, bbox6, resolutions, L, F, log2T)
+            ctx.save_for_backward(x, bbox6, resolutions)
+        ctx.meta = (L, F, log2T, use_sort)
         keep = keep.bool()
         ctx.mark_non_differentiable(keep)
         return out, keep
@@ -160,12 +215,15 @@ class HashEncodeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dkeep):
         x, bbox6, resolutions = ctx.saved_tensors
-        L, F, log2T = ctx.meta
+        L, F, log2T, use_sort = ctx.meta
         T = 1 << log2T
         dflat = torch.zeros(L * T * F, dtype=torch.float32, device=x.device)
-        hash_encode_backward(x, dout, bbox6, resolutions, L, F, log2T, dflat)
+        if use_sort:
+            hash_encode_backward_sorted(x, dout, bbox6, resolutions, L, F, log2T, dflat)
+        else:
+            hash_encode_backward(x, dout, bbox6, resolutions, L, F, log2T, dflat)
         grads = dflat.view(L, T, F).unbind(0)
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 # ----------------------------------------------------------------------------------------------

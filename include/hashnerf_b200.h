@@ -40,7 +40,8 @@ HN_API const char* hn_last_error_string(void);
 HN_API int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Launch-shape knobs for profiling sweeps (not part of the numerical contract): keys "hash_fwd_lpg",
- * "hash_bwd_lpg" (levels per thread: 1,2,4,8,16; 0 = heuristic). */
+ * "hash_bwd_lpg" (levels per thread: 1,2,4,8,16; 0 = heuristic), "hash_bwd_agg" (warp-aggregated scatter:
+ * -1 = for sorted points only, 0 = never, 1 = always). */
 HN_API int hn_set_tuning(const char* key, int value);
 
 /* ---- (a3) spatial hash : embedding/hash_encoding.py:112-128 ------------------------------------ */
@@ -65,6 +66,23 @@ HN_API int hn_hash_encode_fwd(const float* x, const float* tables, const float* 
  * corners.  ACCUMULATES into dtables (caller zeroes).  No gradient w.r.t. x exists on this path. */
 HN_API int hn_hash_encode_bwd(const float* x, const float* dy, const float* bbox, const float* resolutions,
                        int64_t N, int L, int F, int log2T, float* dtables, void* stream);
+
+/* Coherent ("sorted") variant of the two calls above.  hn_hash_sort_points bins the points into a
+ * grid_res^3 grid over the bbox (counting sort, x fastest) and writes xs4[i] = (x, y, z, bit-cast original
+ * row) for the i-th point in cell order; the *_sorted calls process that order -- gathers coalesce / hit L1,
+ * the scatter sums lanes that share a voxel in-warp before issuing atomics -- and read dy / write out, keep at
+ * the ORIGINAL rows, so results are indistinguishable from the plain calls (forward bit-identical, backward
+ * up to atomic summation order).  workspace: hn_hash_sort_workspace_bytes(N, grid_res) bytes, 16-byte aligned;
+ * xs4: [N] float4.  N < 2^32. */
+HN_API int64_t hn_hash_sort_workspace_bytes(int64_t N, int grid_res);
+HN_API int hn_hash_sort_points(const float* x, const float* bbox, int64_t N, int grid_res, void* workspace,
+                               float* xs4, void* stream);
+HN_API int hn_hash_encode_fwd_sorted(const float* xs4, const float* tables, const float* bbox,
+                                     const float* resolutions, int64_t N, int L, int F, int log2T, float* out,
+                                     uint8_t* keep, void* stream);
+HN_API int hn_hash_encode_bwd_sorted(const float* xs4, const float* dy, const float* bbox,
+                                     const float* resolutions, int64_t N, int L, int F, int log2T, float* dtables,
+                                     void* stream);
 
 /* ---- (a7) spherical harmonics : embedding/spherical_harmonic.py:65-103 ------------------------- */
 /* dirs [N,3] -> out [N, degree^2], 1 <= degree <= 5. */

@@ -156,12 +156,46 @@ def test_hash_encode_launch_shapes_agree(lpg):
     close(g1, g2, GRAD_RTOL, atol=1e-6 * g2.abs().max().item())
 
 
+@pytest.mark.parametrize("log2T,bbox,n,agg", [(14, cases.BBOX_ODD, 50_000, -1), (19, cases.BBOX_UNIT, 33_333, -1),
+                                               (12, cases.BBOX_ODD, 257, -1), (19, cases.BBOX_ODD, 40_000, 1)])
+def test_hash_encode_coherent_path_vs_oracle(log2T, bbox, n, agg):
+    """Counting sort + sorted gather + warp-aggregated scatter: forward still bit-exact, gradients within the
+    atomic tolerance; also the aggregated scatter on caller-ordered points (agg=1)."""
+    from hn_b200 import _lib, ops
+    emb, tables = make_embedder(bbox, log2T)
+    emb.coherent = True if agg < 0 else False
+    x = cases.points_in_box(n, bbox, seed=2000 + log2T)
+    if agg > 0:  # ray-like ordering: consecutive points are close, so runs exist without sorting
+        x = x[np.lexsort((x[:, 0], x[:, 1], x[:, 2]))]
+    lo, hi = t(np.float32(bbox[0])), t(np.float32(bbox[1]))
+    want, want_keep = O.hash_encode(t(x), t(tables), lo, hi, O.level_resolutions(), log2T)
+    _lib.set_tuning("hash_bwd_agg", agg)
+    try:
+        out, keep = emb(g32(x))
+        bit_equal(out, want)
+        bit_equal(keep, want_keep)
+        dy = np.random.RandomState(5).randn(n, 32).astype(np.float32)
+        (out * g32(dy)).sum().backward()
+    finally:
+        _lib.set_tuning("hash_bwd_agg", -1)
+    an = O.hash_encode_grad_tables(t(x), t(dy), lo, hi, O.level_resolutions(), log2T, 2)
+    got = torch.stack([e.weight.grad for e in emb.embeddings]).double().cpu()
+    assert (got - an).abs().max().item() <= GRAD_RTOL * an.abs().max().item()
+    # the sort is a permutation of the rows and keeps the coordinates intact
+    xs4 = ops.hash_sort_points(g32(x), emb._geometry(torch.device(DEV))[0], 32)
+    rows = xs4[:, 3].contiguous().view(torch.int32).long()
+    assert torch.equal(torch.sort(rows).values, torch.arange(n, device=DEV))
+    bit_equal(xs4[:, :3], g32(x)[rows])
+
+
 @pytest.mark.parametrize("n", [0, 1, 255, 257])
 def test_hash_encode_ragged_and_empty(n):
     emb, tables = make_embedder(cases.BBOX_ODD, 10)
     x = cases.points_in_box(max(n, 16), cases.BBOX_ODD, 9)[:n]
-    out, keep = emb(g32(x).reshape(n, 3))
-    assert out.shape == (n, 32) and keep.shape == (n,)
+    for coherent in (False, True):
+        emb.coherent = coherent
+        out, keep = emb(g32(x).reshape(n, 3))
+        assert out.shape == (n, 32) and keep.shape == (n,)
     if n:
         want, _ = O.hash_encode(t(x), t(tables), t(np.float32(cases.BBOX_ODD[0])), t(np.float32(cases.BBOX_ODD[1])),
                                 O.level_resolutions(), 10)
@@ -189,6 +223,7 @@ def test_hash_encode_full_size_properties():
     """BASELINE config 2 size (2^24 points, T=19): properties that need no full-size oracle."""
     n, log2T = 1 << 24, 19
     emb, tables = make_embedder(cases.BBOX_UNIT, log2T)
+    assert emb.coherent is None  # default policy: this many points take the sorted (coherent) path
     gen = torch.Generator(device=DEV).manual_seed(0)
     x = torch.rand(n, 3, device=DEV, generator=gen) * 3.0 - 1.5
     out, keep = emb(x)
@@ -211,6 +246,16 @@ def test_hash_encode_full_size_properties():
     out4.backward(dy)
     sums = torch.stack([e.weight.grad.double().sum() for e in emb.embeddings]).cpu().numpy()
     np.testing.assert_allclose(sums, np.full(16, 2.0 * n), rtol=1e-4)
+    # (4) the coherent path and the plain path agree: forward bit-for-bit, gradients to atomic tolerance
+    g_sorted = torch.stack([e.weight.grad for e in emb.embeddings]).clone()
+    emb.coherent = False
+    for e in emb.embeddings:
+        e.weight.grad = None
+    out_plain, _ = emb(x)
+    bit_equal(out_plain.detach(), out4.detach())
+    out_plain.backward(dy)
+    g_plain = torch.stack([e.weight.grad for e in emb.embeddings])
+    assert (g_plain - g_sorted).abs().max().item() <= GRAD_RTOL * g_plain.abs().max().item()
 
 
 # ---------------------------------------------------------------------------------------------- SH
