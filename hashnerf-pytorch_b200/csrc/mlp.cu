@@ -12,40 +12,9 @@
 // their transposes in the backward kernel) live in shared memory and are read as warp-uniform LDS.128
 // broadcasts; a thread's activations live in its private column of two ping-pong shared buffers
 // ([feature][thread], bank == lane, conflict-free), so layers need no barrier between them.
-#include "common.cuh"
+#include "mlp_common.cuh"
 
 namespace hn {
-
-constexpr int kNT = 128;  // threads per CTA == points per tile
-constexpr int kIn = 32, kViews = 16, kHid = 64, kGeo = 15, kH2 = 16, kCin = 31, kCinPad = 32;
-// shared-memory weight image (W2 rows padded 31 -> 32 so every row is float4-aligned)
-constexpr int kW0 = 0;                     // [64][32]
-constexpr int kW1 = kW0 + kHid * kIn;      // [16][64]
-constexpr int kW2 = kW1 + kH2 * kHid;      // [64][32] (padded)
-constexpr int kW3 = kW2 + kHid * kCinPad;  // [64][64]
-constexpr int kW4 = kW3 + kHid * kHid;     // [3][64]
-constexpr int kWTotal = kW4 + 3 * kHid;    // 9408 floats
-// transposed image used by the backward pass: Wt[k][j] = W[j][k]
-constexpr int kT0 = kWTotal;               // [32][64]  (W0^T)
-constexpr int kT1 = kT0 + kIn * kHid;      // [64][16]  (W1^T)
-constexpr int kT2 = kT1 + kHid * kH2;      // [32][64]  (W2^T, padded row 31 = 0)
-constexpr int kT3 = kT2 + kCinPad * kHid;  // [64][64]  (W3^T)
-constexpr int kWBoth = kT3 + kHid * kHid;  // 18624 floats
-// packed global layout (nn.Linear.weight order, unpadded)
-constexpr int kG0 = 0, kG1 = kG0 + 2048, kG2 = kG1 + 1024, kG3 = kG2 + 64 * 31, kG4 = kG3 + 4096;
-static_assert(kG4 + 192 == HN_MLP_PARAMS, "packed weight count");
-
-__device__ __forceinline__ float packed_weight(const float* __restrict__ w, int i) {
-  // i indexes the padded shared image [kW0, kWTotal)
-  if (i < kW1) return __ldg(w + kG0 + i);
-  if (i < kW2) return __ldg(w + kG1 + (i - kW1));
-  if (i < kW3) {
-    const int r = (i - kW2) >> 5, c = (i - kW2) & 31;
-    return (c < kCin) ? __ldg(w + kG2 + r * kCin + c) : 0.f;
-  }
-  if (i < kW4) return __ldg(w + kG3 + (i - kW3));
-  return __ldg(w + kG4 + (i - kW4));
-}
 
 __device__ __forceinline__ void load_weights_to_smem(const float* __restrict__ w, float* __restrict__ sm,
                                                      bool with_transposes) {
@@ -335,6 +304,19 @@ mlp_bwd_weight_kernel(const float* __restrict__ enc, int64_t enc_stride, const f
 constexpr size_t kFwdSmem = (size_t)(kWTotal + 2 * kHid * kNT) * sizeof(float);  // 103,168 B
 constexpr size_t kBwdSmem = (size_t)(kWBoth + 2 * kHid * kNT) * sizeof(float);   // 140,032 B
 
+// tcgen05 implementation (mlp_tc.cu)
+int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
+               const float* weights, const uint8_t* keep, int64_t N, float* out, int aligned, cudaStream_t stream);
+int64_t mlp_tc_bwd_workspace_floats(int64_t N);
+int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
+               const float* weights, const uint8_t* keep, const float* dout, int64_t N, float* d_enc, float* dweights,
+               float* workspace, int aligned, cudaStream_t stream);
+int g_mlp_impl = 1;  // 1 = tcgen05 3xTF32 (mlp_tc.cu, default), 0 = FFMA fp32 (this file)
+
+static inline bool rows16(const float* p, int64_t stride) {
+  return ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && (stride % 4 == 0);
+}
+
 static int ensure_smem_optin() {
   static thread_local int done_dev = -1;
   int dev = 0;
@@ -356,7 +338,9 @@ extern "C" {
 int64_t hn_mlp_bwd_workspace_bytes(int64_t N) {
   if (N <= 0) return 0;
   const int64_t tiles = (N + hn::kNT - 1) / hn::kNT;
-  return tiles * hn::kWsRows * hn::kNT * (int64_t)sizeof(float);
+  const int64_t ffma = tiles * hn::kWsRows * hn::kNT;
+  const int64_t tcw = hn::mlp_tc_bwd_workspace_floats(N);
+  return (ffma > tcw ? ffma : tcw) * (int64_t)sizeof(float);  // either implementation may be selected at run time
 }
 
 int hn_mlp_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
@@ -367,6 +351,9 @@ int hn_mlp_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   if (N == 0) return 0;
   HN_REQUIRE(enc && views && weights && out, "hn_mlp_fwd: null pointer");
   HN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "hn_mlp_fwd: out must be 16-byte aligned");
+  if (hn::g_mlp_impl == 1)
+    return hn::mlp_tc_fwd(enc, enc_stride, views, views_stride, pts_per_view, weights, keep, N, out,
+                          hn::rows16(enc, enc_stride) ? 1 : 0, (cudaStream_t)stream);
   int rc = hn::ensure_smem_optin();
   if (rc) return rc;
   const int64_t tiles = (N + hn::kNT - 1) / hn::kNT;
@@ -387,6 +374,9 @@ int hn_mlp_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   HN_REQUIRE(enc && views && weights && dout && d_enc && dweights && workspace, "hn_mlp_bwd: null pointer");
   HN_REQUIRE(((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(d_enc)) & 15u) == 0,
              "hn_mlp_bwd: dout and d_enc must be 16-byte aligned");
+  if (hn::g_mlp_impl == 1)
+    return hn::mlp_tc_bwd(enc, enc_stride, views, views_stride, pts_per_view, weights, keep, dout, N, d_enc, dweights,
+                          workspace, hn::rows16(enc, enc_stride) ? 1 : 0, (cudaStream_t)stream);
   int rc = hn::ensure_smem_optin();
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;

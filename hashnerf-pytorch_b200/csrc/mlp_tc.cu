@@ -1,0 +1,697 @@
+// mlp_tc.cu -- NeRFSmall on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators and
+// activations in TMEM), 3xTF32 split so that the result keeps fp32-level accuracy.
+//
+// Same contract as mlp.cu (reference models.py:151-174 + the expand/cat/mask of run_nerf_helpers.py:219-225).
+//
+// A CTA of 128 threads owns a tile of 128 points: thread t <-> point t <-> TMEM lane t.  Every layer is
+//   D[128 x N] (TMEM) = A[128 x K] (TMEM) . W[N x K]^T (shared memory, canonical no-swizzle K-major image)
+// issued by one thread as three chains of K/8 MMAs (A_lo.W_hi + A_hi.W_lo + A_hi.W_hi), committed to an
+// mbarrier.  The epilogue is row-private: each thread reads its row of D with tcgen05.ld, applies ReLU /
+// slicing / concatenation in registers, splits into tf32 hi + lo and writes the next layer's A operand straight
+// back into TMEM with tcgen05.st -- activations never touch shared or global memory.  Shared memory holds only
+// the weights (hi and lo images, 76 KB), so two CTAs (= two tiles in flight) fit per SM; TMEM: 192 of the 256
+// columns allocated per CTA (D 64 | A_hi 64 | A_lo 64).
+#include "mlp_common.cuh"
+#include "tc05.cuh"
+
+namespace hn {
+namespace tc {
+
+constexpr int kTile = 128;
+// canonical K-major weight images, in floats: [N][K] each
+constexpr int oW0 = 0;                 // 64 x 32
+constexpr int oW1 = oW0 + 64 * 32;     // 16 x 64
+constexpr int oW2 = oW1 + 16 * 64;     // 64 x 32 (K padded 31 -> 32)
+constexpr int oW3 = oW2 + 64 * 32;     // 64 x 64
+constexpr int oW4 = oW3 + 64 * 64;     //  8 x 64 (N padded 3 -> 8)
+constexpr int kImg = oW4 + 8 * 64;     // 9728 floats per image (hi, then lo)
+constexpr uint32_t kColD = 0, kColAhi = 64, kColAlo = 128, kTmemCols = 256;
+
+__device__ __forceinline__ void stage_matrix(const float* __restrict__ w, int rows, int cols, int rows_pad, int K,
+                                             float* __restrict__ hi_img, float* __restrict__ lo_img) {
+  for (int i = threadIdx.x; i < rows_pad * K; i += blockDim.x) {
+    const int n = i / K, k = i % K;
+    const float v = (n < rows && k < cols) ? __ldg(w + n * cols + k) : 0.f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    hi_img[canon(n, k, K)] = __uint_as_float(hi);
+    lo_img[canon(n, k, K)] = __uint_as_float(lo);
+  }
+}
+
+__device__ __forceinline__ void stage_weights(const float* __restrict__ w, float* __restrict__ smem) {
+  float* hi = smem;
+  float* lo = smem + kImg;
+  stage_matrix(w + kG0, 64, 32, 64, 32, hi + oW0, lo + oW0);
+  stage_matrix(w + kG1, 16, 64, 16, 64, hi + oW1, lo + oW1);
+  stage_matrix(w + kG2, 64, 31, 64, 32, hi + oW2, lo + oW2);
+  stage_matrix(w + kG3, 64, 64, 64, 64, hi + oW3, lo + oW3);
+  stage_matrix(w + kG4, 3, 64, 8, 64, hi + oW4, lo + oW4);
+}
+
+// One layer: D = A . W^T as 3 x (K/8) MMAs; small terms first.  Called by ONE thread.
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t w_hi_saddr, uint32_t w_lo_saddr, int N, int K) {
+  const uint32_t idesc = make_idesc(kTile, N);
+  const uint32_t lbo = 128, sbo = (uint32_t)(K / 4) * 128;
+  uint32_t acc = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = tmem + (pass == 0 ? kColAlo : kColAhi);
+    const uint32_t w = (pass == 1) ? w_lo_saddr : w_hi_saddr;
+#pragma unroll 1
+    for (int s = 0; s < K / 8; ++s) {
+      umma_ts(tmem + kColD, a + 8 * s, make_sdesc(w + s * 256, lbo, sbo), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+// write 16 activations (columns c0 .. c0+15 of this thread's row) as the next layer's A operand
+__device__ __forceinline__ void put16(uint32_t row_taddr, int c0, const float (&v)[16]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split_tf32(v[i], hi[i], lo[i]);
+  tmem_st16(row_taddr + kColAhi + c0, hi);
+  tmem_st16(row_taddr + kColAlo + c0, lo);
+}
+
+// everything a layer boundary needs: stores visible -> the tile's 128 threads arrived -> one of them issues ->
+// all wait.  `sync_id` names the hardware barrier of this tile context (0 = the CTA-wide barrier when the CTA
+// runs a single context); `leader` is true for the context's issuing thread.
+__device__ __forceinline__ void ctx_sync(int sync_id) {
+  if (sync_id == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(sync_id), "r"(kTile) : "memory");
+}
+
+__device__ __forceinline__ void run_layer(uint32_t tmem, uint64_t* bar, uint32_t& phase, uint32_t w_hi, uint32_t w_lo,
+                                          int N, int K, int sync_id = 0, bool leader = (threadIdx.x == 0)) {
+  wait_st();
+  fence_before_sync();
+  ctx_sync(sync_id);
+  if (leader) {
+    fence_after_sync();
+    issue_layer(tmem, w_hi, w_lo, N, K);
+    umma_commit(bar);
+  }
+  mbar_wait(bar, phase);
+  phase ^= 1u;
+  fence_after_sync();
+}
+
+__global__ void __launch_bounds__(kTile, 2)
+mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float* __restrict__ views,
+                  int64_t views_stride, int64_t pts_per_view, const float* __restrict__ weights,
+                  const uint8_t* __restrict__ keep, int64_t N, float* __restrict__ out, int aligned) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  stage_weights(weights, smem);
+  if (t == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t row = tmem + ((uint32_t)(warp * 32) << 16);  // this thread's lane, column 0
+  const uint32_t s_hi = smem_u32(smem), s_lo = smem_u32(smem + kImg);
+  uint32_t phase = 0;
+
+  const int64_t n_tiles = (N + kTile - 1) / kTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t p = tile * kTile + t;
+    const bool valid = p < N;
+    // ---- layer 0 input: the 32 hash features of this point
+    {
+      const float* erow = enc + (valid ? p : 0) * enc_stride;
+#pragma unroll
+      for (int c0 = 0; c0 < kIn; c0 += 16) {
+        float v[16];
+        if (aligned) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(erow + c0) + q);
+            v[4 * q] = f.x;
+            v[4 * q + 1] = f.y;
+            v[4 * q + 2] = f.z;
+            v[4 * q + 3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __ldg(erow + c0 + i);
+        }
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        put16(row, c0, v);
+      }
+    }
+    run_layer(tmem, &bar, phase, s_hi + oW0 * 4, s_lo + oW0 * 4, 64, 32);  // h1 pre-activation
+#pragma unroll
+    for (int c0 = 0; c0 < kHid; c0 += 16) {
+      float v[16];
+      tmem_ld16(row + kColD + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      put16(row, c0, v);
+    }
+    fence_before_sync();  // D has been read: the next MMA may overwrite it after the barrier
+    run_layer(tmem, &bar, phase, s_hi + oW1 * 4, s_lo + oW1 * 4, 16, 64);  // h2 = [sigma | geo]
+    float sigma;
+    {
+      float h2[16];
+      tmem_ld16(row + kColD, h2);
+      sigma = h2[0];
+      // c = [views(16) | geo(15) | 0]
+      float v[16];
+      const float* vrow = views + ((valid ? p : 0) / pts_per_view) * views_stride;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = valid ? __ldg(vrow + i) : 0.f;
+      put16(row, 0, v);
+#pragma unroll
+      for (int i = 0; i < 15; ++i) v[i] = h2[1 + i];
+      v[15] = 0.f;
+      put16(row, 16, v);
+    }
+    fence_before_sync();
+    run_layer(tmem, &bar, phase, s_hi + oW2 * 4, s_lo + oW2 * 4, 64, 32);  // h3
+#pragma unroll
+    for (int c0 = 0; c0 < kHid; c0 += 16) {
+      float v[16];
+      tmem_ld16(row + kColD + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      put16(row, c0, v);
+    }
+    fence_before_sync();
+    run_layer(tmem, &bar, phase, s_hi + oW3 * 4, s_lo + oW3 * 4, 64, 64);  // h4
+#pragma unroll
+    for (int c0 = 0; c0 < kHid; c0 += 16) {
+      float v[16];
+      tmem_ld16(row + kColD + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      put16(row, c0, v);
+    }
+    fence_before_sync();
+    run_layer(tmem, &bar, phase, s_hi + oW4 * 4, s_lo + oW4 * 4, 8, 64);  // rgb (N padded to 8)
+    {
+      float rgb[8];
+      tmem_ld8(row + kColD, rgb);
+      if (valid) {
+        const float s = (keep != nullptr && keep[p] == 0) ? 0.f : sigma;  // run_nerf_helpers.py:225
+        reinterpret_cast<float4*>(out)[p] = make_float4(rgb[0], rgb[1], rgb[2], s);
+      }
+    }
+    fence_before_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+constexpr size_t kFwdSmemBytes = (size_t)2 * kImg * sizeof(float);  // 77,824
+
+// ================================================================================================
+// backward, kernel 1: recompute + dX chain, all on tcgen05, activations/deltas resident in TMEM.
+// Everything the weight gradients need is written feature-major to the workspace:
+//   per 128-point tile a [472][128] fp32 block; row r, point p at  r * 128 + p  (coalesced across the warp)
+// ================================================================================================
+constexpr int rH1 = 0, rC = 64, rH3 = 96, rH4 = 160, rDz1 = 224, rDh2 = 288, rDz3 = 304, rDz4 = 368, rIn = 432,
+              rDrgb = 464, kWsRowsTc = 472;
+// transposed weight images for the dX chain (canonical K-major [N][K]), appended after the forward images
+constexpr int oT4 = kImg;                // 64 x 8   : (n = hidden k, kk = c)      = W4[c][k]
+constexpr int oT3 = oT4 + 64 * 8;        // 64 x 64  : (n = k, kk = j)             = W3[j][k]
+constexpr int oT2 = oT3 + 64 * 64;       // 16 x 64  : (n = geo index, kk = j)     = W2[j][16 + n]   (n = 15: zero)
+constexpr int oT1 = oT2 + 16 * 64;       // 64 x 16  : (n = k, kk = j)             = W1[j][k]
+constexpr int oT0 = oT1 + 64 * 16;       // 32 x 64  : (n = k, kk = j)             = W0[j][k]
+constexpr int kImgBwd = oT0 + 32 * 64;   // 18432 floats per image
+constexpr size_t kDeltaSmemBytes = (size_t)2 * kImgBwd * sizeof(float);  // 147,456
+
+// image(n, kk) = W[kk][col0 + n] for n < n_valid (W is [rows_w][cols_w] row-major), zero otherwise
+__device__ __forceinline__ void stage_transposed(const float* __restrict__ w, int cols_w, int rows_w, int col0,
+                                                 int n_valid, int n_rows, int K, float* __restrict__ hi_img,
+                                                 float* __restrict__ lo_img) {
+  for (int i = threadIdx.x; i < n_rows * K; i += blockDim.x) {
+    const int n = i / K, kk = i % K;
+    const float v = (n < n_valid && kk < rows_w) ? __ldg(w + kk * cols_w + col0 + n) : 0.f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    hi_img[canon(n, kk, K)] = __uint_as_float(hi);
+    lo_img[canon(n, kk, K)] = __uint_as_float(lo);
+  }
+}
+
+template <bool RELU>
+__device__ __forceinline__ uint64_t epilogue64(uint32_t row, float* __restrict__ ws_col, uint64_t gate, bool gated) {
+  // reads this thread's 64 accumulator columns, applies ReLU (returning the positive mask) or the gate,
+  // stores to the workspace column (stride 128) and writes the next A operand
+  uint64_t mask = 0;
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+    tmem_ld16(row + kColD + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (RELU) {
+        if (v[i] > 0.f) mask |= (1ull << (c0 + i));
+        v[i] = fmaxf(v[i], 0.f);
+      }
+      if (gated) v[i] = ((gate >> (c0 + i)) & 1ull) ? v[i] : 0.f;
+      ws_col[(c0 + i) * kTile] = v[i];
+    }
+    put16(row, c0, v);
+  }
+  return mask;
+}
+
+// Two tile contexts of 128 threads share one copy of the weight images (144 KB) and interleave on the SM:
+// while one context waits for its MMA chain the other runs its epilogue.
+__global__ void __launch_bounds__(2 * kTile, 1)
+mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const float* __restrict__ views,
+                        int64_t views_stride, int64_t pts_per_view, const float* __restrict__ weights,
+                        const uint8_t* __restrict__ keep, const float* __restrict__ dout, int64_t N,
+                        float* __restrict__ d_enc, float* __restrict__ ws, int aligned) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  const int ctx = threadIdx.x / kTile, t = threadIdx.x % kTile, warp = t >> 5;
+  const int sync_id = 1 + ctx;
+  const bool leader = (t == 0);
+  uint64_t* bar_p = &bars[ctx];
+  {
+    float* hi = smem;
+    float* lo = smem + kImgBwd;
+    stage_matrix(weights + kG0, 64, 32, 64, 32, hi + oW0, lo + oW0);
+    stage_matrix(weights + kG1, 16, 64, 16, 64, hi + oW1, lo + oW1);
+    stage_matrix(weights + kG2, 64, 31, 64, 32, hi + oW2, lo + oW2);
+    stage_matrix(weights + kG3, 64, 64, 64, 64, hi + oW3, lo + oW3);
+    stage_transposed(weights + kG4, 64, 3, 0, 64, 64, 8, hi + oT4, lo + oT4);
+    stage_transposed(weights + kG3, 64, 64, 0, 64, 64, 64, hi + oT3, lo + oT3);
+    stage_transposed(weights + kG2, 31, 64, 16, 15, 16, 64, hi + oT2, lo + oT2);
+    stage_transposed(weights + kG1, 64, 16, 0, 64, 64, 16, hi + oT1, lo + oT1);
+    stage_transposed(weights + kG0, 32, 64, 0, 32, 32, 64, hi + oT0, lo + oT0);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 2 * kTmemCols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot + (uint32_t)ctx * kTmemCols;
+  const uint32_t row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t s_hi = smem_u32(smem), s_lo = smem_u32(smem + kImgBwd);
+  uint32_t phase = 0;
+
+  const int64_t n_tiles = (N + kTile - 1) / kTile;
+  for (int64_t tile = (int64_t)blockIdx.x * 2 + ctx; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
+    const int64_t p = tile * kTile + t;
+    const bool valid = p < N;
+    float* g = ws + tile * (int64_t)(kWsRowsTc * kTile) + t;  // this point's workspace column
+    // ---- inputs
+    {
+      const float* erow = enc + (valid ? p : 0) * enc_stride;
+#pragma unroll
+      for (int c0 = 0; c0 < kIn; c0 += 16) {
+        float v[16];
+        if (aligned) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(erow + c0) + q);
+            v[4 * q] = f.x;
+            v[4 * q + 1] = f.y;
+            v[4 * q + 2] = f.z;
+            v[4 * q + 3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __ldg(erow + c0 + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (!valid) v[i] = 0.f;
+          g[(rIn + c0 + i) * kTile] = v[i];
+        }
+        put16(row, c0, v);
+      }
+    }
+    float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) go = __ldg(reinterpret_cast<const float4*>(dout) + p);
+    const float dsigma = (valid && !(keep != nullptr && keep[p] == 0)) ? go.w : 0.f;
+    g[(rDrgb + 0) * kTile] = go.x;
+    g[(rDrgb + 1) * kTile] = go.y;
+    g[(rDrgb + 2) * kTile] = go.z;
+#pragma unroll
+    for (int i = 3; i < 8; ++i) g[(rDrgb + i) * kTile] = 0.f;
+
+    // ---- forward recompute
+    run_layer(tmem, bar_p, phase, s_hi + oW0 * 4, s_lo + oW0 * 4, 64, 32, sync_id, leader);
+    const uint64_t m1 = epilogue64<true>(row, g + rH1 * kTile, 0, false);
+    fence_before_sync();
+    run_layer(tmem, bar_p, phase, s_hi + oW1 * 4, s_lo + oW1 * 4, 16, 64, sync_id, leader);
+    {
+      float h2[16];
+      tmem_ld16(row + kColD, h2);
+      float v[16];
+      const float* vrow = views + ((valid ? p : 0) / pts_per_view) * views_stride;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] = valid ? __ldg(vrow + i) : 0.f;
+        g[(rC + i) * kTile] = v[i];
+      }
+      put16(row, 0, v);
+#pragma unroll
+      for (int i = 0; i < 15; ++i) v[i] = h2[1 + i];
+      v[15] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[(rC + 16 + i) * kTile] = v[i];
+      put16(row, 16, v);
+    }
+    fence_before_sync();
+    run_layer(tmem, bar_p, phase, s_hi + oW2 * 4, s_lo + oW2 * 4, 64, 32, sync_id, leader);
+    const uint64_t m3 = epilogue64<true>(row, g + rH3 * kTile, 0, false);
+    fence_before_sync();
+    run_layer(tmem, bar_p, phase, s_hi + oW3 * 4, s_lo + oW3 * 4, 64, 64, sync_id, leader);
+    uint64_t m4 = 0;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {  // h4: only its values (for dW4) and its mask are needed
+      float v[16];
+      tmem_ld16(row + kColD + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (v[i] > 0.f) m4 |= (1ull << (c0 + i));
+        g[(rH4 + c0 + i) * kTile] = fmaxf(v[i], 0.f);
+      }
+    }
+    // ---- backward chain
+    {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      v[0] = go.x;
+      v[1] = go.y;
+      v[2] = go.z;
+      put16(row, 0, v);  // A = drgb, K = 8 (columns 3..7 zero)
+    }
+    fence_before_sync();
+    run_layer(tmem, bar_p, phase, s_hi + oT4 * 4, s_lo + oT4 * 4, 64, 8, sync_id, leader);    // dh4 = drgb . W4
+    epilogue64<false>(row, g + rDz4 * kTile, m4, true);                      // dz4 = dh4 . [h4 > 0]
+    fence_before_sync();
+    run_layer(tmem, bar_p, phase, s_hi + oT3 * 4, s_lo + oT3 * 4, 64, 64, sync_id, leader);   // dh3 = dz4 . W3
+    epilogue64<false>(row, g + rDz3 * kTile, m3, true);                      // dz3
+    fence_before_sync();
+    run_layer(tmem, bar_p, phase, s_hi + oT2 * 4, s_lo + oT2 * 4, 16, 64, sync_id, leader);   // dgeo = (dz3 . W2)[16:31]
+    {
+      float dg[16], v[16];
+      tmem_ld16(row + kColD, dg);
+      v[0] = dsigma;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) v[1 + i] = dg[i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[(rDh2 + i) * kTile] = v[i];
+      put16(row, 0, v);  // A = dh2, K = 16
+    }
+    fence_before_sync();
+    run_layer(tmem, bar_p, phase, s_hi + oT1 * 4, s_lo + oT1 * 4, 64, 16, sync_id, leader);   // dh1 = dh2 . W1
+    epilogue64<false>(row, g + rDz1 * kTile, m1, true);                      // dz1
+    fence_before_sync();
+    run_layer(tmem, bar_p, phase, s_hi + oT0 * 4, s_lo + oT0 * 4, 32, 64, sync_id, leader);   // d_enc = dz1 . W0
+#pragma unroll
+    for (int c0 = 0; c0 < kIn; c0 += 16) {
+      float v[16];
+      tmem_ld16(row + kColD + c0, v);
+      if (valid) {
+        float* drow = d_enc + p * kIn + c0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(drow)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+    fence_before_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_slot, 2 * kTmemCols);
+}
+
+// ================================================================================================
+// backward, kernel 2: weight gradients on tcgen05.  dW[j][k] = sum_p D[p][j] * A[p][k] is an MMA with the
+// POINTS as the K dimension; the feature-major workspace rows are exactly K-major operands.  M = 64 feature
+// rows, N = the other tensor's features, K = 8 points per instruction.  Accumulators stay in TMEM for the
+// whole kernel (152 columns) and are flushed once with atomics.  A CTA streams 64-point half tiles:
+// load rows -> split hi/lo -> canonical image in shared memory -> 3 x 8 MMAs per matrix.
+// ================================================================================================
+constexpr int kHalf = 64;
+constexpr uint32_t cW0 = 0, cW1 = 32, cW2 = 48, cW3 = 80, cW4 = 144;  // accumulator columns
+constexpr size_t kWeightSmemBytes = (size_t)4 * 64 * kHalf * sizeof(float);  // M_hi | M_lo | N_hi | N_lo  (64 KB)
+
+// Staging of one operand pair for a 64-point half tile.  Slot s of thread t covers float4 number s*128 + t of
+// the pair: the first 1024 belong to the 64 M-side rows, the rest to the N-side rows.  Within an operand,
+// consecutive indices walk (row % 8, 16-byte chunk, row group) so that the 8 lanes of one chunk fill one
+// 128-byte core matrix (conflict-free STS.128) while reading 64 contiguous bytes per row.
+constexpr int kSlots = 16;  // (64 + 64 rows) * 16 chunks / 128 threads
+
+struct PairDesc {
+  int m_row, n_row, n_rows;
+  uint32_t col;
+};
+
+__device__ __forceinline__ void prefetch_pair(const float* __restrict__ base, const PairDesc& pr, float4 (&reg)[kSlots]) {
+  const int total = (64 + pr.n_rows) * (kHalf / 4);
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int idx = s * kTile + threadIdx.x;
+    reg[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < total) {
+      const bool is_n = idx >= 64 * (kHalf / 4);
+      const int i = is_n ? idx - 64 * (kHalf / 4) : idx;
+      const int r8 = i & 7, rest = i >> 3;
+      const int chunk = rest % (kHalf / 4), rg = rest / (kHalf / 4);
+      const int r = (is_n ? pr.n_row : pr.m_row) + rg * 8 + r8;
+      reg[s] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * kTile) + chunk);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_pair(const PairDesc& pr, const float4 (&reg)[kSlots], float* __restrict__ Mhi,
+                                           float* __restrict__ Mlo, float* __restrict__ Nhi, float* __restrict__ Nlo) {
+  const int total = (64 + pr.n_rows) * (kHalf / 4);
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int idx = s * kTile + threadIdx.x;
+    if (idx < total) {
+      const bool is_n = idx >= 64 * (kHalf / 4);
+      const int i = is_n ? idx - 64 * (kHalf / 4) : idx;
+      const int r8 = i & 7, rest = i >> 3;
+      const int chunk = rest % (kHalf / 4), rg = rest / (kHalf / 4);
+      const int off = (rg * (kHalf / 4) + chunk) * 32 + r8 * 4;
+      uint32_t h[4], l[4];
+      split_tf32(reg[s].x, h[0], l[0]);
+      split_tf32(reg[s].y, h[1], l[1]);
+      split_tf32(reg[s].z, h[2], l[2]);
+      split_tf32(reg[s].w, h[3], l[3]);
+      *reinterpret_cast<uint4*>((is_n ? Nhi : Mhi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>((is_n ? Nlo : Mlo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTile, 2)
+mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restrict__ dweights) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  float* Mhi = smem;
+  float* Mlo = Mhi + 64 * kHalf;
+  float* Nhi = Mlo + 64 * kHalf;
+  float* Nlo = Nhi + 64 * kHalf;
+  if (t == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  uint32_t phase = 0;
+  bool pending = false;   // an MMA group reading the staging buffers is in flight
+  uint32_t fresh = 0x1f;  // bit i set: accumulator i has not been written yet (first MMA overwrites)
+
+  // (M-side rows, N-side rows): dW0 = dz1^T.in, dW1^T = h1^T.dh2, dW2 = dz3^T.c, dW3 = dz4^T.h3, dW4^T = h4^T.drgb
+  const PairDesc pairs[5] = {{rDz1, rIn, 32, cW0}, {rH1, rDh2, 16, cW1}, {rDz3, rC, 32, cW2}, {rDz4, rH3, 64, cW3},
+                             {rH4, rDrgb, 8, cW4}};
+  const int64_t n_half = ((N + kTile - 1) / kTile) * 2;
+  const int64_t my_first = blockIdx.x;
+  float4 reg[kSlots];
+  if (my_first < n_half)
+    prefetch_pair(ws + (my_first >> 1) * (int64_t)(kWsRowsTc * kTile) + (my_first & 1) * kHalf, pairs[0], reg);
+  for (int64_t h = my_first; h < n_half; h += gridDim.x) {
+    const float* base = ws + (h >> 1) * (int64_t)(kWsRowsTc * kTile) + (h & 1) * kHalf;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const PairDesc pr = pairs[i];
+      if (pending) {  // the previous MMAs must have consumed the staging buffers
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        pending = false;
+      }
+      store_pair(pr, reg, Mhi, Mlo, Nhi, Nlo);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (t == 0) {
+        fence_after_sync();
+        const uint32_t idesc = make_idesc(64, pr.n_rows);
+        const uint32_t lbo = 128, sbo = (kHalf / 4) * 128;
+        uint32_t acc = ((fresh >> i) & 1u) ? 0u : 1u;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = smem_u32(pass == 0 ? Mlo : Mhi);
+          const uint32_t b = smem_u32(pass == 1 ? Nlo : Nhi);
+#pragma unroll 1
+          for (int s = 0; s < kHalf / 8; ++s) {
+            umma_ss(tmem + pr.col, make_sdesc(a + s * 256, lbo, sbo), make_sdesc(b + s * 256, lbo, sbo), idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&bar);
+      }
+      fresh &= ~(1u << i);
+      pending = true;
+      // global loads of the next pair fly while the tensor core works on this one
+      if (i < 4) {
+        prefetch_pair(base, pairs[i + 1], reg);
+      } else if (h + gridDim.x < n_half) {
+        const int64_t hn = h + gridDim.x;
+        prefetch_pair(ws + (hn >> 1) * (int64_t)(kWsRowsTc * kTile) + (hn & 1) * kHalf, pairs[0], reg);
+      }
+    }
+  }
+  if (pending) {
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+  }
+  fence_after_sync();
+  // ---- flush: M = 64 accumulators keep row m in lane (m % 16) + 32 * (m / 16)
+  const bool any = blockIdx.x < n_half;
+  const int m = warp * 16 + lane;  // valid for lane < 16
+  const uint32_t row = tmem + ((uint32_t)(warp * 32) << 16);
+  if (any) {
+    float v[16];
+    // dW0[j = m][k]   (64 x 32)
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      tmem_ld16(row + cW0 + c0, v);
+      if (lane < 16)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(dweights + kG0 + m * 32 + c0 + i, v[i]);
+    }
+    // dW1^T[k = m][j] -> dW1[j][k]   (16 x 64)
+    tmem_ld16(row + cW1, v);
+    if (lane < 16)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) atomicAdd(dweights + kG1 + i * 64 + m, v[i]);
+    // dW2[j = m][c]   (64 x 31)
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      tmem_ld16(row + cW2 + c0, v);
+      if (lane < 16)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < 31) atomicAdd(dweights + kG2 + m * 31 + c0 + i, v[i]);
+    }
+    // dW3[j = m][k]   (64 x 64)
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      tmem_ld16(row + cW3 + c0, v);
+      if (lane < 16)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(dweights + kG3 + m * 64 + c0 + i, v[i]);
+    }
+    // dW4^T[k = m][c] -> dW4[c][k]   (3 x 64)
+    {
+      float u[8];
+      tmem_ld8(row + cW4, u);
+      if (lane < 16)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(dweights + kG4 + c * 64 + m, u[c]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace tc
+
+int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
+               const float* weights, const uint8_t* keep, int64_t N, float* out, int aligned, cudaStream_t stream) {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail((int)e, "cudaGetDevice");
+  if (done_dev != dev) {
+    e = cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kFwdSmemBytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_fwd_kernel)");
+    done_dev = dev;
+  }
+  const int64_t tiles = (N + tc::kTile - 1) / tc::kTile;
+  const int64_t cap = (int64_t)sm_count() * 2;
+  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+  tc::mlp_tc_fwd_kernel<<<grid, tc::kTile, tc::kFwdSmemBytes, stream>>>(enc, enc_stride, views, views_stride,
+                                                                       pts_per_view, weights, keep, N, out, aligned);
+  return check_launch("mlp_tc_fwd_kernel");
+}
+
+int64_t mlp_tc_bwd_workspace_floats(int64_t N) {
+  const int64_t tiles = (N + tc::kTile - 1) / tc::kTile;
+  return tiles * tc::kWsRowsTc * tc::kTile;
+}
+
+int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
+               const float* weights, const uint8_t* keep, const float* dout, int64_t N, float* d_enc, float* dweights,
+               float* workspace, int aligned, cudaStream_t stream) {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail((int)e, "cudaGetDevice");
+  if (done_dev != dev) {
+    e = cudaFuncSetAttribute(tc::mlp_tc_bwd_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)tc::kDeltaSmemBytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_delta_kernel)");
+    e = cudaFuncSetAttribute(tc::mlp_tc_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)tc::kWeightSmemBytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_weight_kernel)");
+    done_dev = dev;
+  }
+  const int64_t tiles = (N + tc::kTile - 1) / tc::kTile;
+  {
+    const int64_t cap = (int64_t)sm_count();
+    const int64_t want = (tiles + 1) / 2;  // two tile contexts per CTA
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    tc::mlp_tc_bwd_delta_kernel<<<grid, 2 * tc::kTile, tc::kDeltaSmemBytes, stream>>>(
+        enc, enc_stride, views, views_stride, pts_per_view, weights, keep, dout, N, d_enc, workspace, aligned);
+    int rc = check_launch("mlp_tc_bwd_delta_kernel");
+    if (rc) return rc;
+  }
+  {
+    const int64_t halves = tiles * 2;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    const unsigned grid = (unsigned)(halves < cap ? halves : cap);
+    tc::mlp_tc_bwd_weight_kernel<<<grid, tc::kTile, tc::kWeightSmemBytes, stream>>>(N, workspace, dweights);
+    return check_launch("mlp_tc_bwd_weight_kernel");
+  }
+}
+
+}  // namespace hn

@@ -41,7 +41,8 @@ HN_API int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Launch-shape knobs for profiling sweeps (not part of the numerical contract): keys "hash_fwd_lpg",
  * "hash_bwd_lpg" (levels per thread: 1,2,4,8,16; 0 = heuristic), "hash_bwd_agg" (warp-aggregated scatter:
- * -1 = for sorted points only, 0 = never, 1 = always). */
+ * -1 = for sorted points only, 0 = never, 1 = always), "hash_agg_max_heads", "hash_level_major", "mlp_impl"
+ * (1 = tcgen05 3xTF32 tensor-core MLP, the default; 0 = FFMA fp32 MLP). */
 HN_API int hn_set_tuning(const char* key, int value);
 
 /* ---- (a3) spatial hash : embedding/hash_encoding.py:112-128 ------------------------------------ */

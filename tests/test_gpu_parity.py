@@ -269,7 +269,16 @@ def test_sh_golden(golden):
 
 
 # ---------------------------------------------------------------------------------------------- MLP
-def test_mlp_golden(golden):
+@pytest.fixture(params=[1, 0], ids=["tcgen05_3xtf32", "ffma_fp32"])
+def mlp_impl(request):
+    """Both MLP implementations must meet the same bar: the tcgen05 (default) and the FFMA fp32 one."""
+    from hn_b200 import _lib
+    _lib.set_tuning("mlp_impl", request.param)
+    yield request.param
+    _lib.set_tuning("mlp_impl", 1)
+
+
+def test_mlp_golden(golden, mlp_impl):
     g = golden("mlp")
     net = make_mlp([g[f"w{i}"] for i in range(5)])
     x = g32(g["x"]).requires_grad_(True)
@@ -283,7 +292,7 @@ def test_mlp_golden(golden):
 
 
 @pytest.mark.parametrize("n,per_ray", [(1, 1), (127, 1), (129, 1), (64 * 50, 64), (192 * 7, 192)])
-def test_mlp_vs_oracle(n, per_ray):
+def test_mlp_vs_oracle(n, per_ray, mlp_impl):
     sig, col = cases.mlp_weights(70 + n % 7)
     net = make_mlp(sig + col)
     rs = np.random.RandomState(n)
