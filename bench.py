@@ -158,7 +158,7 @@ def workload_config(args, n_points):
 # ------------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------------
-def train_step_extra(dev, n_rand, steps=8, warmup=3):
+def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False):
     """BASELINE configs[2]/[3] shape: full coarse+fine render + loss + backward + RAdam on synthetic rays."""
     from embedding.hash_encoding import HashEmbedder
     from embedding.spherical_harmonic import SHEncoder
@@ -180,14 +180,29 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3):
     target = torch.rand(n_rand, 3, device=dev, generator=g)
     qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
 
-    def step():
-        ret = render_rays(rays, coarse, qfn, 64, embed_fn=emb, retraw=True, perturb=1., N_importance=128,
-                          network_fine=fine, white_bkgd=True)
-        opt.zero_grad()
-        loss = img2mse(ret["rgb_map"], target) + img2mse(ret["rgb0"], target) \
+    def render_fn(rb):
+        return render_rays(rb, coarse, qfn, 64, embed_fn=emb, retraw=True, perturb=1., N_importance=128,
+                           network_fine=fine, white_bkgd=True)
+
+    def loss_fn(ret, tgt):
+        return img2mse(ret["rgb_map"], tgt) + img2mse(ret["rgb0"], tgt) \
             + 1e-10 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum())
-        loss.backward()
-        opt.step()
+
+    if graphed:
+        from hn_b200.graph import GraphedTrainStep
+        trainer = GraphedTrainStep(n_rand, render_fn, loss_fn, opt, dev, warmup=2)
+
+        def step():
+            trainer.step(rays, target)
+        for _ in range(4):  # eager warm-up + capture happen outside the timed region
+            step()
+    else:
+        def step():
+            ret = render_fn(rays)
+            opt.zero_grad()
+            loss = loss_fn(ret, target)
+            loss.backward()
+            opt.step()
 
     ms = time_loop(step, steps, warmup) / steps
     return n_rand / ms * 1e3, ms
@@ -340,7 +355,12 @@ def run_ours(args):
             rps, ms = train_step_extra(dev, n_rand)
             extra[f"train_rays_per_s_nrand{n_rand}"] = round(rps, 1)
             extra[f"train_ms_per_step_nrand{n_rand}"] = round(ms, 3)
-        extra["train_step"] = "render_rays 64+128 samples/ray, perturb=1, white_bkgd, mse+sparsity, backward, RAdam (no TV)"
+            rps, ms = train_step_extra(dev, n_rand, steps=20, graphed=True)
+            extra[f"train_rays_per_s_nrand{n_rand}_cuda_graph"] = round(rps, 1)
+            extra[f"train_ms_per_step_nrand{n_rand}_cuda_graph"] = round(ms, 3)
+        extra["train_step"] = ("render_rays 64+128 samples/ray, perturb=1, white_bkgd, mse+sparsity, backward, RAdam "
+                               "(no TV); eager = the drop-in API as run_nerf.py drives it, cuda_graph = "
+                               "hn_b200.graph.GraphedTrainStep replaying the same kernels")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

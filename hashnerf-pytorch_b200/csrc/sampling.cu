@@ -106,6 +106,103 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
   }
 }
 
+// Fused hierarchical resampling for one ray per warp (run_nerf_helpers.py:547-552, 568):
+//   mids = .5 (z[1:] + z[:-1]);  samples = sample_pdf(mids, weights[1:-1], u);  merged = sort(cat(z, samples));
+//   z_std = std(samples, unbiased=False).
+// Shared memory per warp: cdf[S-1] | mids[S-1] | sort buffer[npad].
+__global__ void __launch_bounds__(128)
+resample_kernel(const float* __restrict__ z, const float* __restrict__ weights, const float* __restrict__ u,
+                const float* __restrict__ u_det, int64_t R, int S, int Ni, int npad, float* __restrict__ samples,
+                float* __restrict__ merged, float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= R) return;
+  const int nb = S - 1;
+  float* cdf = smem + (size_t)warp * (2 * nb + npad);
+  float* mids = cdf + nb;
+  float* buf = mids + nb;
+  const float* zr = z + r * S;
+  const float* wr = weights + r * S + 1;  // weights[..., 1:-1]
+
+  for (int i = lane; i < nb; i += 32) mids[i] = __fmul_rn(0.5f, __fadd_rn(__ldg(zr + i + 1), __ldg(zr + i)));  // :547
+  float part = 0.f;
+  for (int i = lane; i < nb - 1; i += 32) part += __ldg(wr + i) + 1e-5f;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(kFullMask, part, off);
+  const float total = part;
+  float carry = 0.f;
+  if (lane == 0) cdf[0] = 0.f;
+  for (int base = 0; base < nb - 1; base += 32) {
+    const int i = base + lane;
+    float v = (i < nb - 1) ? (__ldg(wr + i) + 1e-5f) / total : 0.f;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float t = __shfl_up_sync(kFullMask, v, off);
+      if (lane >= off) v += t;
+    }
+    if (i < nb - 1) cdf[i + 1] = carry + v;
+    carry += __shfl_sync(kFullMask, v, 31);
+  }
+  // sort buffer: the S coarse depths, then the Ni new samples, then +inf padding
+  for (int i = lane; i < S; i += 32) buf[i] = __ldg(zr + i);
+  for (int i = S + Ni + lane; i < npad; i += 32) buf[i] = __int_as_float(0x7f800000);
+  __syncwarp();
+
+  float s1 = 0.f;
+  for (int k = lane; k < Ni; k += 32) {
+    const float uu = u ? __ldg(u + r * Ni + k) : __ldg(u_det + k);
+    int lo = 0, hi = nb;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] > uu) hi = mid;
+      else lo = mid + 1;
+    }
+    const int below = max(lo - 1, 0), above = min(lo, nb - 1);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float b0 = mids[below], b1 = mids[above];
+    float denom = __fsub_rn(c1, c0);
+    if (denom < 1e-5f) denom = 1.f;
+    const float t = __fdiv_rn(__fsub_rn(uu, c0), denom);
+    const float smp = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+    samples[r * Ni + k] = smp;
+    buf[S + k] = smp;
+    s1 += smp;
+  }
+  if (z_std != nullptr) {  // population standard deviation of the new samples (:568)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s1 += __shfl_xor_sync(kFullMask, s1, off);
+    const float mean = s1 / (float)Ni;
+    __syncwarp();
+    float s2 = 0.f;
+    for (int k = lane; k < Ni; k += 32) {
+      const float d = buf[S + k] - mean;
+      s2 = fmaf(d, d, s2);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(kFullMask, s2, off);
+    if (lane == 0) z_std[r] = sqrtf(s2 / (float)Ni);
+  }
+  __syncwarp();
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < npad; i += 32) {
+        const int partner = i ^ j;
+        if (partner > i) {
+          const float x = buf[i], y = buf[partner];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) {
+            buf[i] = y;
+            buf[partner] = x;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < S + Ni; i += 32) merged[r * (S + Ni) + i] = buf[i];
+}
+
 // Block per row, bitonic network over the row padded to a power of two with +inf.
 __global__ void sort_concat_rows_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb,
                                         int npad, float* __restrict__ out) {
@@ -179,6 +276,25 @@ int hn_sample_pdf(const float* bins, const float* weights, const float* u, const
   hn::sample_pdf_kernel<<<(unsigned)((R + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
       bins, weights, u, u_det, R, nb, Ni, samples);
   return hn::check_launch("sample_pdf_kernel");
+}
+
+int hn_resample(const float* z, const float* weights, const float* u, const float* u_det, int64_t R, int S, int Ni,
+                float* samples, float* merged, float* z_std, void* stream) {
+  HN_REQUIRE(R >= 0 && S >= 3 && Ni >= 1, "hn_resample: need S >= 3 and Ni >= 1");
+  HN_REQUIRE(S + Ni <= 2048, "hn_resample: S + Ni must be <= 2048");
+  if (R == 0) return 0;
+  HN_REQUIRE(z && weights && samples && merged && (u || u_det), "hn_resample: null pointer");
+  int npad = 2;
+  while (npad < S + Ni) npad <<= 1;
+  const int warps = 4;
+  const size_t smem = (size_t)warps * (2 * (S - 1) + npad) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(hn::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return hn::fail((int)e, "cudaFuncSetAttribute(resample_kernel)");
+  }
+  hn::resample_kernel<<<(unsigned)((R + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
+      z, weights, u, u_det, R, S, Ni, npad, samples, merged, z_std);
+  return hn::check_launch("resample_kernel");
 }
 
 int hn_sort_concat_rows(const float* a, int na, const float* b, int nb, int64_t R, float* out, void* stream) {

@@ -70,6 +70,10 @@ class HashEmbedder(nn.Module):
         # None: re-order large batches by grid cell before encoding (results unchanged, see ops.HashEncodeFn);
         # True / False force the choice.
         self.coherent = None
+        # True: backward accumulates in place into one persistent flat gradient buffer and points
+        # embeddings[l].weight.grad at its slices (see ops.GradSink); False: plain autograd gradients.
+        self.fused_grad_accumulation = True
+        self._sink = None
 
     # -- storage --------------------------------------------------------------------------------
     def _level_weights(self):
@@ -120,12 +124,22 @@ class HashEmbedder(nn.Module):
     # -- forward --------------------------------------------------------------------------------
     def forward(self, x):
         """x: [N,3] points -> (features [N, n_levels*F], keep_mask [N] bool)  (hash_encoding.py:84-110)."""
+        feats, keep = self.encode(x)
+        return feats, keep.bool()
+
+    def encode(self, x):
+        """Same as forward() but the mask stays the kernel's uint8 (what the fused MLP consumes)."""
         lead = x.shape[:-1]
         pts = x.reshape(-1, 3)
         box, res = self._geometry(pts.device)
         self._flatten_parameters()
+        sink = None
+        if self.fused_grad_accumulation and torch.is_grad_enabled():
+            if self._sink is None or any(a is not b for a, b in zip(self._sink.params, self._level_weights())):
+                self._sink = ops.GradSink(self._level_weights())
+            sink = self._sink
         feats, keep = ops.HashEncodeFn.apply(pts, box, res, self.log2_hashmap_size, self.n_features_per_level,
-                                             self.coherent, *self._level_weights())
+                                             self.coherent, sink, *self._level_weights())
         if len(lead) != 1:
             feats, keep = feats.reshape(*lead, self.out_dim), keep.reshape(lead)
         return feats, keep

@@ -37,9 +37,11 @@ SIGNATURES = {
     "hn_composite_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "hn_composite_bwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hn_sample_pdf": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p]),
+    "hn_resample": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p]),
     "hn_sort_concat_rows": (_i, [_p, _i, _p, _i, _l, _p, _p]),
     "hn_coarse_z": (_i, [_p, _p, _l, _p, _p, _l, _i, _i, _p, _p]),
     "hn_ray_points": (_i, [_p, _p, _l, _p, _l, _i, _p, _p]),
+    "hn_radam_step_dev": (_i, [_p, _p, _p, _p, _l, _p, _p]),
     "hn_radam_step": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _i, _f, _p]),
 }
 

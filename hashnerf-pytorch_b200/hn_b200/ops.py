@@ -185,18 +185,71 @@ def sort_grid_res(n_points: int) -> int:
     return int(min(256, max(16, round(n_points ** (1.0 / 3.0)))))
 
 
+class GradSink:
+    """Persistent flat gradient buffer behind a group of parameters that are views of one flat buffer.
+
+    ``torch.autograd`` would hand every backward call a fresh dense gradient per parameter and add them up
+    (for the 16 level tables: a 64 MiB memset plus 16 adds per pass).  Instead the backward kernels accumulate
+    straight into this buffer and ``param.grad`` is pointed at its slices, which is also what lets RAdam and
+    the data-parallel all-reduce treat the group as ONE tensor.  Semantics are those of autograd: gradients
+    accumulate until ``zero_grad()``; both ``set_to_none=True`` (buffer re-zeroed on the next backward) and
+    ``set_to_none=False`` (slices zeroed in place) work, and gradients produced by other autograd paths
+    (e.g. the TV loss through ``nn.Embedding``) are merged."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        self.flat = None
+
+    def _slices(self):
+        out, off = [], 0
+        for p in self.params:
+            out.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return out
+
+    def acquire(self) -> torch.Tensor:
+        """Flat fp32 buffer to accumulate into; afterwards every param.grad is a slice of it."""
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        if self.flat is None or self.flat.device != dev or self.flat.numel() != n:
+            self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            fresh = True
+        else:
+            fresh = False
+        slices = self._slices()
+        mine = [p.grad is not None and p.grad.data_ptr() == s.data_ptr() and p.grad.shape == s.shape
+                for p, s in zip(self.params, slices)]
+        if all(mine):
+            return self.flat                      # still accumulating into our buffer
+        foreign = [(s, p.grad) for p, s, m in zip(self.params, slices, mine) if (not m) and p.grad is not None]
+        if not fresh:
+            if any(mine):                         # mixed state: keep what is ours, clear the rest
+                for p, s, m in zip(self.params, slices, mine):
+                    if not m:
+                        s.zero_()
+            else:
+                self.flat.zero_()                 # first backward since zero_grad(set_to_none=True)
+        for s, g in foreign:                      # gradients that arrived through plain autograd
+            s.add_(g)
+        for p, s in zip(self.params, slices):
+            p.grad = s
+        return self.flat
+
+
 class HashEncodeFn(torch.autograd.Function):
-    """features, keep = HashEncodeFn.apply(x, bbox6, resolutions, log2T, F, coherent, *level_tables)
+    """features, keep = HashEncodeFn.apply(x, bbox6, resolutions, log2T, F, coherent, sink, *level_tables)
 
     ``level_tables`` are the L ``nn.Embedding.weight`` parameters ([2^T, F] each).  Autograd routes the
     table gradient to each of them; the gradients returned are slices of ONE flat buffer filled by a
     single scatter kernel (the reference produces 16 separate dense gradients through
     embedding_dense_backward, hash_encoding.py:106).  ``coherent``: None = sort the points by grid cell when
-    there are many of them, True / False = force."""
+    there are many of them, True / False = force.  ``sink``: a GradSink (gradients accumulate in place into its
+    persistent buffer and ``param.grad`` points at it) or None (plain autograd return values)."""
 
     @staticmethod
-    def forward(ctx, x, bbox6, resolutions, log2T, F, coherent, *level_tables):
+    def forward(ctx, x, bbox6, resolutions, log2T, F, coherent, sink, *level_tables):
         L = len(level_tables)
+        ctx.sink = sink
         flat = pack(level_tables)
         N = x.shape[0]
         use_sort = (N >= SORT_MIN_POINTS) if coherent is None else (bool(coherent) and N > 0)
@@ -208,22 +261,24 @@ class HashEncodeFn(torch.autograd.Function):
             out, keep = hash_encode_forward(x, flat, bbox6, resolutions, L, F, log2T)
             ctx.save_for_backward(x, bbox6, resolutions)
         ctx.meta = (L, F, log2T, use_sort)
-        keep = keep.bool()
         ctx.mark_non_differentiable(keep)
-        return out, keep
+        return out, keep  # keep: uint8 (HashEmbedder.forward converts to bool for the caller)
 
     @staticmethod
     def backward(ctx, dout, _dkeep):
         x, bbox6, resolutions = ctx.saved_tensors
         L, F, log2T, use_sort = ctx.meta
         T = 1 << log2T
-        dflat = torch.zeros(L * T * F, dtype=torch.float32, device=x.device)
+        sink = ctx.sink
+        dflat = sink.acquire() if sink is not None else torch.zeros(L * T * F, dtype=torch.float32, device=x.device)
         if use_sort:
             hash_encode_backward_sorted(x, dout, bbox6, resolutions, L, F, log2T, dflat)
         else:
             hash_encode_backward(x, dout, bbox6, resolutions, L, F, log2T, dflat)
+        if sink is not None:  # accumulated in place; param.grad already points into the buffer
+            return (None,) * (7 + L)
         grads = dflat.view(L, T, F).unbind(0)
-        return (None, None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None, None) + tuple(grads)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -253,10 +308,11 @@ def _rows(t: torch.Tensor, width: int) -> Tuple[torch.Tensor, int]:
 
 
 class MLPFn(torch.autograd.Function):
-    """out[N,4] = MLPFn.apply(enc[N,32], views[Nv,16], pts_per_view, keep|None, W0, W1, W2, W3, W4)"""
+    """out[N,4] = MLPFn.apply(enc[N,32], views[Nv,16], pts_per_view, keep|None, sink|None, W0, W1, W2, W3, W4)"""
 
     @staticmethod
-    def forward(ctx, enc, views, pts_per_view, keep, *weights):
+    def forward(ctx, enc, views, pts_per_view, keep, sink, *weights):
+        ctx.sink = sink
         dev = _need_cuda(enc, views, *weights)
         enc_r, enc_stride = _rows(enc, 32)
         views_r, views_stride = _rows(views, 16)
@@ -264,7 +320,7 @@ class MLPFn(torch.autograd.Function):
         if views_r.shape[0] * pts_per_view < N:
             raise RuntimeError("views has too few rows for pts_per_view")
         wflat = pack(weights)
-        keep_u8 = None if keep is None else keep.to(torch.uint8).contiguous()
+        keep_u8 = None if keep is None else (keep if keep.dtype == torch.uint8 else keep.to(torch.uint8)).contiguous()
         out = torch.empty(N, 4, dtype=torch.float32, device=dev)
         with _on(dev):
             _lib.call("hn_mlp_fwd", enc_r.data_ptr(), enc_stride, views_r.data_ptr(), views_stride,
@@ -281,18 +337,21 @@ class MLPFn(torch.autograd.Function):
         dev = enc_r.device
         dout = _f32c(dout)
         d_enc = torch.empty(N, 32, dtype=torch.float32, device=dev)
-        dflat = torch.zeros(MLP_PARAMS, dtype=torch.float32, device=dev)
+        sink = ctx.sink
+        dflat = sink.acquire() if sink is not None else torch.zeros(MLP_PARAMS, dtype=torch.float32, device=dev)
         lib = _lib.load()
         ws = torch.empty(max(1, lib.hn_mlp_bwd_workspace_bytes(N) // 4), dtype=torch.float32, device=dev)
         with _on(dev):
             _lib.call("hn_mlp_bwd", enc_r.data_ptr(), enc_stride, views_r.data_ptr(), views_stride, ppv,
                       wflat.data_ptr(), keep_u8.data_ptr() if has_keep else None, dout.data_ptr(), N,
                       d_enc.data_ptr(), dflat.data_ptr(), ws.data_ptr(), _stream())
+        if sink is not None:
+            return (d_enc, None, None, None, None) + (None,) * 5
         grads, off = [], 0
         for (o, i) in MLP_SHAPES:
             grads.append(dflat[off:off + o * i].view(o, i))
             off += o * i
-        return (d_enc, None, None, None) + tuple(grads)
+        return (d_enc, None, None, None, None) + tuple(grads)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -354,6 +413,25 @@ def sample_pdf(bins, weights, n_samples: int, u: Optional[torch.Tensor] = None,
         _lib.call("hn_sample_pdf", bins.data_ptr(), weights.data_ptr(), _ptr(u), _ptr(u_det), R, nb, int(n_samples),
                   out.data_ptr(), _stream())
     return out
+
+
+@torch.no_grad()
+def resample(z, weights, n_importance: int, u: Optional[torch.Tensor] = None, u_det: Optional[torch.Tensor] = None):
+    """(z_samples [R,Ni], z_merged [R,S+Ni], z_std [R]) -- the resampling block of render_rays in one launch."""
+    dev = _need_cuda(z, weights, u, u_det)
+    z, weights = _f32c(z), _f32c(weights)
+    R, S = z.shape
+    if u is not None:
+        u = _f32c(u)
+    else:
+        u_det = _f32c(u_det)
+    samples = torch.empty(R, n_importance, dtype=torch.float32, device=dev)
+    merged = torch.empty(R, S + n_importance, dtype=torch.float32, device=dev)
+    z_std = torch.empty(R, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_resample", z.data_ptr(), weights.data_ptr(), _ptr(u), _ptr(u_det), R, S, int(n_importance),
+                  samples.data_ptr(), merged.data_ptr(), z_std.data_ptr(), _stream())
+    return samples, merged, z_std
 
 
 @torch.no_grad()

@@ -41,6 +41,8 @@ class NeRFSmall(nn.Module):
                 "(run_nerf_helpers.py:79-84: num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, "
                 f"input_ch=32, input_ch_views=16); got layer shapes {got}")
         self._flatten_parameters()
+        self.fused_grad_accumulation = True  # see ops.GradSink
+        self._sink = None
 
     def _weights(self):
         return [l.weight for l in self.sigma_net] + [l.weight for l in self.color_net]
@@ -78,7 +80,12 @@ class NeRFSmall(nn.Module):
         """enc [N,32]; views [ceil(N/pts_per_view),16] (one row per ray); keep [N] bool or None (sigma is
         zeroed where False, run_nerf_helpers.py:225)."""
         self._flatten_parameters()
-        return ops.MLPFn.apply(enc, views, pts_per_view, keep, *self._weights())
+        sink = None
+        if self.fused_grad_accumulation and torch.is_grad_enabled():
+            if self._sink is None or any(a is not b for a, b in zip(self._sink.params, self._weights())):
+                self._sink = ops.GradSink(self._weights())
+            sink = self._sink
+        return ops.MLPFn.apply(enc, views, pts_per_view, keep, sink, *self._weights())
 
 
 class _OutOfScope(nn.Module):

@@ -58,23 +58,19 @@ class RAdam(Optimizer):
             st['exp_avg_sq'] = v[off:off + p.numel()].view_as(p)
             off += p.numel()
 
-    @torch.no_grad()
-    def step(self, closure=None):
-        loss = None
-        if closure is not None:
-            with torch.enable_grad():
-                loss = closure()
+    def _spans(self):
+        """[(group, [params])]: maximal runs of parameters whose data, gradients and moments are each back to
+        back in one storage and whose step counts agree -- each run is updated by one kernel launch."""
+        out = []
         for group in self.param_groups:
-            beta1, beta2 = group['betas']
             active = [p for p in group['params'] if p.grad is not None]
             for p in active:
                 if p.grad.is_sparse:
                     raise RuntimeError('RAdam does not support sparse gradients')
                 if not p.is_cuda or p.dtype != torch.float32:
                     raise RuntimeError("hashnerf_b200 RAdam updates fp32 CUDA parameters only (no CPU fallback)")
-            # split into runs of parameters that are consecutive in memory
             runs, cur = [], []
-            for p in active:
+            for p in active:  # runs of parameters that are consecutive in memory
                 if cur and ops._consecutive([cur[-1], p]):
                     cur.append(p)
                 else:
@@ -84,50 +80,88 @@ class RAdam(Optimizer):
             if cur:
                 runs.append(cur)
             for run in runs:
-                if any(len(self.state[p]) == 0 for p in run):
-                    fresh = [p for p in run if len(self.state[p]) == 0]
-                    if len(fresh) == len(run):
-                        self._init_state(run)
-                    else:
-                        for p in fresh:
-                            self._init_state([p])
-                self._update_run(group, run, beta1, beta2)
-        return loss
+                fresh = [p for p in run if len(self.state[p]) == 0]
+                if len(fresh) == len(run):
+                    self._init_state(run)
+                else:
+                    for p in fresh:
+                        self._init_state([p])
+                for p in run:
+                    st = self.state[p]
+                    if st['exp_avg'].dtype != torch.float32 or not st['exp_avg'].is_contiguous():
+                        st['exp_avg'] = st['exp_avg'].float().contiguous()
+                        st['exp_avg_sq'] = st['exp_avg_sq'].float().contiguous()
+                    if not p.grad.is_contiguous():
+                        p.grad = p.grad.contiguous()
+                i = 0
+                while i < len(run):
+                    j = i + 1
+                    st0 = self.state[run[i]]
+                    while j < len(run):
+                        a, b = run[j - 1], run[j]
+                        sa, sb = self.state[a], self.state[b]
+                        if not (sb['step'] == st0['step'] and ops._consecutive([a.grad, b.grad])
+                                and ops._consecutive([sa['exp_avg'], sb['exp_avg']])
+                                and ops._consecutive([sa['exp_avg_sq'], sb['exp_avg_sq']])):
+                            break
+                        j += 1
+                    out.append((group, run[i:j]))
+                    i = j
+        return out
 
-    def _update_run(self, group, run, beta1, beta2):
-        # fuse the longest prefixes whose grads / moments are also consecutive and whose step counts agree
-        i = 0
-        while i < len(run):
-            j = i + 1
-            st0 = self.state[run[i]]
-            while j < len(run):
-                a, b = run[j - 1], run[j]
-                sa, sb = self.state[a], self.state[b]
-                ok = (sb['step'] == st0['step']
-                      and ops._consecutive([a.grad, b.grad])
-                      and ops._consecutive([sa['exp_avg'], sb['exp_avg']])
-                      and ops._consecutive([sa['exp_avg_sq'], sb['exp_avg_sq']]))
-                if not ok:
-                    break
-                j += 1
-            span = run[i:j]
-            first = span[0]
-            for p in span:
-                st = self.state[p]
-                st['step'] += 1
-                if st['exp_avg'].dtype != torch.float32 or not st['exp_avg'].is_contiguous():
-                    st['exp_avg'] = st['exp_avg'].float().contiguous()
-                    st['exp_avg_sq'] = st['exp_avg_sq'].float().contiguous()
-            step = self.state[first]['step']
-            mode, step_size = self._rectification(step, beta1, beta2)
+    def _advance(self, group, span):
+        """Host side of one update: bump the step counters, return (mode, step_size) (radam.py:61-78)."""
+        for p in span:
+            self.state[p]['step'] += 1
+        beta1, beta2 = group['betas']
+        return self._rectification(self.state[span[0]]['step'], beta1, beta2)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group, span in self._spans():
+            mode, step_size = self._advance(group, span)
+            beta1, beta2 = group['betas']
+            first, st = span[0], self.state[span[0]]
             n = sum(p.numel() for p in span)
-            grad = first.grad if first.grad.is_contiguous() else None
-            if grad is None:
-                assert len(span) == 1
-                grad = first.grad.contiguous()
-            st = self.state[first]
             with ops._on(first.device):
-                _lib.call("hn_radam_step", first.data_ptr(), grad.data_ptr(), st['exp_avg'].data_ptr(),
+                _lib.call("hn_radam_step", first.data_ptr(), first.grad.data_ptr(), st['exp_avg'].data_ptr(),
                           st['exp_avg_sq'].data_ptr(), n, beta1, beta2, group['eps'], group['lr'],
                           group['weight_decay'], step_size, mode, self.grad_scale, ops._stream())
-            i = j
+        return loss
+
+    # ---- CUDA-graph support ------------------------------------------------------------------------
+    # A captured graph replays kernel launches, not Python.  The step-dependent scalars therefore live in a
+    # device array refreshed by a (captured) copy from pinned host memory:
+    #     opt.graph_plan()            once, gradients present, before capture
+    #     opt.graph_launch()          inside the capture
+    #     opt.graph_prepare()         before every replay (host only: counters, lr schedule -> pinned array)
+    @torch.no_grad()
+    def graph_plan(self):
+        self._g_spans = self._spans()
+        dev = self._g_spans[0][1][0].device
+        self._g_host = torch.zeros(len(self._g_spans), 8, dtype=torch.float32).pin_memory()
+        self._g_dev = torch.zeros(len(self._g_spans), 8, dtype=torch.float32, device=dev)
+
+    def graph_prepare(self):
+        for i, (group, span) in enumerate(self._g_spans):
+            mode, step_size = self._advance(group, span)
+            beta1, beta2 = group['betas']
+            row = self._g_host[i]
+            row[0], row[1], row[2] = beta1, beta2, group['eps']
+            row[3] = group['weight_decay'] * group['lr']
+            row[4] = step_size * group['lr']
+            row[5], row[6] = self.grad_scale, float(mode)
+
+    @torch.no_grad()
+    def graph_launch(self):
+        self._g_dev.copy_(self._g_host, non_blocking=True)
+        for i, (group, span) in enumerate(self._g_spans):
+            first, st = span[0], self.state[span[0]]
+            n = sum(p.numel() for p in span)
+            with ops._on(first.device):
+                _lib.call("hn_radam_step_dev", first.data_ptr(), first.grad.data_ptr(), st['exp_avg'].data_ptr(),
+                          st['exp_avg_sq'].data_ptr(), n, self._g_dev[i].data_ptr(), ops._stream())

@@ -56,14 +56,16 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     ray and handed to the fused MLP together with the keep mask; any other combination of callables goes
     through the generic expand / cat / mask sequence of the reference."""
     flat = inputs.reshape(-1, inputs.shape[-1])
-    embedded, keep_mask = embed_fn(flat)
     per_ray = inputs.shape[-2] if inputs.dim() >= 3 else 1
 
-    if isinstance(fn, NeRFSmall) and viewdirs is not None and isinstance(embeddirs_fn, SHEncoder) \
-            and embeddirs_fn.degree == 4 and viewdirs.shape[0] * per_ray == flat.shape[0]:
-        out = fn.forward_fused(embedded, embeddirs_fn(viewdirs), per_ray, keep_mask)
+    if isinstance(fn, NeRFSmall) and isinstance(embed_fn, HashEmbedder) and viewdirs is not None \
+            and isinstance(embeddirs_fn, SHEncoder) and embeddirs_fn.degree == 4 \
+            and viewdirs.shape[0] * per_ray == flat.shape[0]:
+        embedded, keep_u8 = embed_fn.encode(flat)
+        out = fn.forward_fused(embedded, embeddirs_fn(viewdirs), per_ray, keep_u8)
         return out.reshape(*inputs.shape[:-1], 4)
 
+    embedded, keep_mask = embed_fn(flat)
     if viewdirs is not None:
         dirs = viewdirs[:, None].expand(inputs.shape).reshape(-1, inputs.shape[-1])
         embedded = torch.cat([embedded, embeddirs_fn(dirs)], -1)
@@ -176,24 +178,40 @@ def create_nerf(args):
 # ----------------------------------------------------------------------------------------------
 # hierarchical sampling / compositing
 # ----------------------------------------------------------------------------------------------
+_LINSPACE = {}
+
+
+def _linspace01(steps, dev):
+    """torch.linspace(0, 1, steps) on ``dev``, cached (it is recomputed by the reference on every call)."""
+    key = (int(steps), dev.type, dev.index)
+    t = _LINSPACE.get(key)
+    if t is None:
+        t = _LINSPACE[key] = torch.linspace(0., 1., steps=steps, device=dev)
+    return t
+
+
+def _uniform_variates(R, n, det, pytest, dev):
+    """(u [R,n] or None, u_det [n] or None) exactly as sample_pdf draws them (run_nerf_helpers.py:270-287)."""
+    if pytest:  # fixed numpy variates
+        np.random.seed(0)
+        if det:
+            u = np.broadcast_to(np.linspace(0., 1., n), (R, n))
+        else:
+            u = np.random.rand(R, n)
+        return torch.Tensor(np.ascontiguousarray(u)).to(dev), None
+    if det:
+        return None, _linspace01(n, dev)
+    return torch.rand(R, n, device=dev), None
+
+
 def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
     """Inverse-transform sampling of the piecewise-constant pdf given by ``weights`` over ``bins``
     (run_nerf_helpers.py:264-307): bins [R,nb], weights [R,nb-1] -> samples [R,N_samples]."""
     lead = bins.shape[:-1]
     b2 = bins.reshape(-1, bins.shape[-1])
     w2 = weights.reshape(-1, weights.shape[-1])
-    R = b2.shape[0]
-    if pytest:  # fixed numpy variates, as :279-287
-        np.random.seed(0)
-        if det:
-            u = np.broadcast_to(np.linspace(0., 1., N_samples), (R, N_samples))
-        else:
-            u = np.random.rand(R, N_samples)
-        out = ops.sample_pdf(b2, w2, N_samples, u=torch.Tensor(np.ascontiguousarray(u)).to(b2.device))
-    elif det:
-        out = ops.sample_pdf(b2, w2, N_samples, u_det=torch.linspace(0., 1., steps=N_samples, device=b2.device))
-    else:
-        out = ops.sample_pdf(b2, w2, N_samples, u=torch.rand(R, N_samples, device=b2.device))
+    u, u_det = _uniform_variates(b2.shape[0], N_samples, det, pytest, b2.device)
+    out = ops.sample_pdf(b2, w2, N_samples, u=u, u_det=u_det)
     return out.reshape(*lead, N_samples)
 
 
@@ -234,10 +252,11 @@ def render_rays(ray_batch,
     rb = ray_batch if (ray_batch.dtype == torch.float32 and ray_batch.is_contiguous()) else ray_batch.float().contiguous()
     R, width = rb.shape
     rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]
-    viewdirs = rb[:, -3:] if width > 8 else None
+    rays_d_c = rays_d.contiguous()                       # one packed copy shared by both compositing passes
+    viewdirs = rb[:, -3:].contiguous() if width > 8 else None
     dev = rb.device
 
-    t_vals = torch.linspace(0., 1., steps=N_samples, device=dev)
+    t_vals = _linspace01(N_samples, dev)
     t_rand = None
     if perturb > 0.:
         if pytest:  # :531-534
@@ -250,19 +269,19 @@ def render_rays(ray_batch,
 
     raw = network_query_fn(pts, viewdirs, network_fn)
     rgb_map, disp_map, acc_map, weights, depth_map, sparsity_loss = raw2outputs(
-        raw, z_vals, rays_d, raw_noise_std, white_bkgd, pytest=pytest)
+        raw, z_vals, rays_d_c, raw_noise_std, white_bkgd, pytest=pytest)
 
     if N_importance > 0:
         rgb_map_0, depth_map_0, acc_map_0, sparsity_loss_0 = rgb_map, depth_map, acc_map, sparsity_loss
-        z_vals_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
-        z_samples = sample_pdf(z_vals_mid, weights[..., 1:-1].detach(), N_importance, det=(perturb == 0.),
-                               pytest=pytest)
-        z_vals = ops.sort_concat_rows(z_vals, z_samples)                                      # :551
+        # :547-552 and :568 in one launch: mids, sample_pdf(weights[..., 1:-1]), sort(cat), std
+        det = (perturb == 0.)
+        u, u_det = _uniform_variates(R, N_importance, det, pytest, dev)
+        z_samples, z_vals, z_std = ops.resample(z_vals, weights.detach(), N_importance, u=u, u_det=u_det)
         pts = ops.ray_points(rays_o, rays_d, width, z_vals)                                   # :552
         run_fn = network_fn if network_fine is None else network_fine
         raw = network_query_fn(pts, viewdirs, run_fn)
         rgb_map, disp_map, acc_map, weights, depth_map, sparsity_loss = raw2outputs(
-            raw, z_vals, rays_d, raw_noise_std, white_bkgd, pytest=pytest)
+            raw, z_vals, rays_d_c, raw_noise_std, white_bkgd, pytest=pytest)
 
     ret = {'rgb_map': rgb_map, 'depth_map': depth_map, 'acc_map': acc_map, 'sparsity_loss': sparsity_loss}
     if retraw:
@@ -272,7 +291,7 @@ def render_rays(ray_batch,
         ret['depth0'] = depth_map_0
         ret['acc0'] = acc_map_0
         ret['sparsity_loss0'] = sparsity_loss_0
-        ret['z_std'] = torch.std(z_samples, dim=-1, unbiased=False)
+        ret['z_std'] = z_std
     if DEBUG:
         for k, v in ret.items():
             if torch.isnan(v).any() or torch.isinf(v).any():

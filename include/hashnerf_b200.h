@@ -128,6 +128,11 @@ HN_API int hn_composite_bwd(const float* raw, const float* z, const float* rays_
  * samples [R,Ni]. */
 HN_API int hn_sample_pdf(const float* bins, const float* weights, const float* u, const float* u_det, int64_t R,
                   int nb, int Ni, float* samples, void* stream);
+/* Fused form of the resampling block of render_rays (:547-552, :568): mids, sample_pdf on weights[:,1:-1],
+ * sort(cat(z, samples)) and std(samples).  z, weights [R,S]; u [R,Ni] or NULL (then u_det [Ni]); outputs
+ * samples [R,Ni], merged [R,S+Ni], z_std [R] (may be NULL).  S + Ni <= 2048. */
+HN_API int hn_resample(const float* z, const float* weights, const float* u, const float* u_det, int64_t R, int S,
+                       int Ni, float* samples, float* merged, float* z_std, void* stream);
 /* out[r,:] = sort(cat(a[r,:na], b[r,:nb]))  (run_nerf_helpers.py:551); na+nb <= 2048. */
 HN_API int hn_sort_concat_rows(const float* a, int na, const float* b, int nb, int64_t R, float* out, void* stream);
 
@@ -148,6 +153,10 @@ HN_API int hn_ray_points(const float* rays_o, const float* rays_d, int64_t ray_s
 HN_API int hn_radam_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
                          float eps, float lr, float weight_decay, float step_size, int mode, float grad_scale,
                          void* stream);
+
+/* CUDA-graph friendly form: the step-dependent scalars come from device memory,
+ * hp = {beta1, beta2, eps, weight_decay*lr, step_size*lr, grad_scale, mode, unused}. */
+HN_API int hn_radam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hp, void* stream);
 
 #ifdef __cplusplus
 }

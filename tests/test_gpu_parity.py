@@ -384,6 +384,25 @@ def test_sample_pdf_golden(golden):
     close(got, g["samples_det"], 0, atol=width, what="det: never further than one bin")
 
 
+@pytest.mark.parametrize("R,S,Ni,det", [(50, 64, 128, False), (33, 64, 64, True), (7, 24, 40, False), (5, 3, 1, False)])
+def test_resample_fused(R, S, Ni, det):
+    """The fused resampling launch == mids + sample_pdf(weights[:,1:-1]) + sort(cat) + std, stage by stage."""
+    from hn_b200 import ops
+    rs = np.random.RandomState(R + S)
+    z = np.sort(2 + 4 * rs.rand(R, S).astype(np.float32), -1)
+    w = (rs.rand(R, S).astype(np.float32)) ** 4
+    u = None if det else rs.rand(R, Ni).astype(np.float32)
+    mids = 0.5 * (t(z)[:, 1:] + t(z)[:, :-1])
+    want = O.sample_pdf(mids, t(w)[:, 1:-1], O.det_u(R, Ni) if det else t(u))
+    kw = dict(u_det=torch.linspace(0., 1., steps=Ni, device=DEV)) if det else dict(u=g32(u))
+    samples, merged, z_std = ops.resample(g32(z), g32(w), Ni, **kw)
+    width = float(np.max(z[:, 1:] - z[:, :-1]))
+    mostly_close(samples, want, FWD_RTOL, 2e-5, 0.99, what="samples")
+    close(samples, want, 0, atol=width, what="never further than one bin")
+    bit_equal(merged, torch.sort(torch.cat([g32(z), samples], -1), -1).values)
+    close(z_std, torch.std(samples, dim=-1, unbiased=False), 1e-4, atol=1e-6)
+
+
 def test_sort_concat_rows():
     from hn_b200 import ops
     for na, nb, R in [(64, 128, 100), (1, 1, 3), (5, 0, 4), (24, 40, 48), (700, 1300, 5), (64, 64, 1000)]:
@@ -487,6 +506,65 @@ def test_tv_loss_golden(golden):
         dense = np.zeros((1 << 12, 2), np.float32)
         dense[g[f"l{level}_grad_rows"]] = g[f"l{level}_grad_vals"]
         close(emb.embeddings[level].weight.grad, dense, GRAD_RTOL, atol=1e-9)
+
+
+def test_grad_sink_accumulation_semantics():
+    """Backward accumulates in place into one flat buffer: two passes sum, zero_grad in both flavours resets,
+    gradients arriving through plain autograd (TV loss via nn.Embedding) are merged, RAdam sees one span."""
+    from hn_b200 import _lib
+    from radam import RAdam
+    emb, tables = make_embedder(cases.BBOX_ODD, 10)
+    x1 = g32(cases.points_in_box(3000, cases.BBOX_ODD, 1))
+    x2 = g32(cases.points_in_box(5000, cases.BBOX_ODD, 2))
+    dy1, dy2 = torch.randn(3000, 32, device=DEV), torch.randn(5000, 32, device=DEV)
+
+    def reference(parts):
+        ref, _ = make_embedder(cases.BBOX_ODD, 10)
+        ref.fused_grad_accumulation = False
+        tot = None
+        for xx, dd in parts:
+            for e in ref.embeddings:
+                e.weight.grad = None
+            ref(xx)[0].backward(dd)
+            g = torch.stack([e.weight.grad for e in ref.embeddings])
+            tot = g if tot is None else tot + g
+        return tot
+
+    # coarse + fine style: two forward/backward pairs before the optimizer
+    (emb(x1)[0] * dy1).sum().backward()
+    (emb(x2)[0] * dy2).sum().backward()
+    got = torch.stack([e.weight.grad for e in emb.embeddings])
+    want = reference([(x1, dy1), (x2, dy2)])
+    close(got, want, GRAD_RTOL, atol=1e-6 * want.abs().max().item())
+    flat = emb._sink.flat
+    assert all(e.weight.grad.data_ptr() == flat[i * 2048:].data_ptr() for i, e in enumerate(emb.embeddings))
+
+    opt = RAdam([{"params": list(emb.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+    before = _lib.launches
+    opt.step()
+    assert _lib.launches - before == 1, "the 16 level tables must be updated by one fused launch"
+
+    opt.zero_grad()                                   # set_to_none=True
+    assert all(e.weight.grad is None for e in emb.embeddings)
+    (emb(x1)[0] * dy1).sum().backward()
+    close(torch.stack([e.weight.grad for e in emb.embeddings]), reference([(x1, dy1)]), GRAD_RTOL, atol=1e-9)
+
+    opt.zero_grad(set_to_none=False)                  # in-place zeroing of our slices
+    (emb(x2)[0] * dy2).sum().backward()
+    close(torch.stack([e.weight.grad for e in emb.embeddings]), reference([(x2, dy2)]), GRAD_RTOL, atol=1e-9)
+
+    # a gradient that arrives through nn.Embedding first (as the TV loss does) is merged, not lost
+    opt.zero_grad()
+    idx = torch.arange(0, 64, device=DEV)
+    emb.embeddings[3](idx).sum().backward()
+    (emb(x1)[0] * dy1).sum().backward()
+    want = reference([(x1, dy1)])
+    want[3, :64] += 1.0
+    close(torch.stack([e.weight.grad for e in emb.embeddings]), want, GRAD_RTOL, atol=1e-9)
+    emb.embeddings[3](idx).sum().backward()           # ... and after: autograd adds in place into our slice
+    want[3, :64] += 1.0
+    close(torch.stack([e.weight.grad for e in emb.embeddings]), want, GRAD_RTOL, atol=1e-9)
+    assert emb.embeddings[3].weight.grad.data_ptr() == emb._sink.flat[3 * 2048:].data_ptr()
 
 
 # ---------------------------------------------------------------------------------------------- errors
