@@ -1,0 +1,111 @@
+"""Data parallelism on real GPUs (needs >= 2): two NCCL ranks, each rendering its shard of the rays, must end
+up -- after GradSync.all_reduce -- with the gradient a single process computes on the whole batch, and after
+RAdam(grad_scale = 1/world) with identical parameters on both ranks."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _build(dev):
+    import cases
+    from embedding.hash_encoding import HashEmbedder
+    from embedding.spherical_harmonic import SHEncoder
+    from models import NeRFSmall
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    tables = cases.synth_tables(16, 12, 2) * np.float32(3000.0)
+    emb = HashEmbedder((torch.tensor(cases.BBOX_UNIT[0]), torch.tensor(cases.BBOX_UNIT[1])), log2_hashmap_size=12)
+    with torch.no_grad():
+        for l in range(16):
+            emb.embeddings[l].weight.copy_(T(tables[l]))
+    emb.to(dev)
+    nets = []
+    for seed in (1, 2):
+        sig, col = cases.mlp_weights(seed)
+        net = NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                        input_ch=32, input_ch_views=16)
+        with torch.no_grad():
+            for lin, w in zip(list(net.sigma_net) + list(net.color_net), sig + col):
+                lin.weight.copy_(T(w))
+        nets.append(net.to(dev))
+    return emb, nets, SHEncoder()
+
+
+def _loss_and_backward(emb, nets, sh, rays):
+    from run_nerf_helpers import render_rays, run_network
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    ret = render_rays(rays, nets[0], qfn, 16, embed_fn=emb, retraw=True, perturb=0., N_importance=16,
+                      network_fine=nets[1], white_bkgd=True)
+    loss = ret["rgb_map"].square().sum() + ret["rgb0"].square().sum() + 1e-3 * ret["sparsity_loss"].sum()
+    loss.backward()   # a SUM over rays: per-rank gradients add up to the full-batch gradient
+    return loss
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import cases
+        from hn_b200 import dp
+        from radam import RAdam
+        rays = torch.from_numpy(cases.rays(96, 7)).to(dev)
+        emb, nets, sh = _build(dev)
+        params = list(emb.parameters()) + [p for n in nets for p in n.parameters()]
+        dp.broadcast_parameters(params)
+        s, e = dp.shard_range(rays.shape[0], rank, world)
+        _loss_and_backward(emb, nets, sh, rays[s:e].contiguous())
+        sync = dp.GradSync(params)
+        sync.all_reduce()
+        sync.wait()
+        assert sync.calls_last == 3, f"expected 3 flat all-reduces (tables, coarse MLP, fine MLP), got {sync.calls_last}"
+        got = torch.cat([p.grad.reshape(-1) for p in params]).clone()
+        # single-process reference on the whole batch, same device
+        emb2, nets2, sh2 = _build(dev)
+        _loss_and_backward(emb2, nets2, sh2, rays)
+        want = torch.cat([p.grad.reshape(-1) for p in list(emb2.parameters()) + [p for n in nets2 for p in n.parameters()]])
+        err = (got - want).abs().max().item() / want.abs().max().item()
+        assert err < 1e-4, f"sharded + all-reduced gradient differs from the full-batch gradient: {err}"
+        # averaged update, identical on every rank
+        opt = RAdam([{"params": [p for n in nets for p in n.parameters()], "weight_decay": 1e-6},
+                     {"params": list(emb.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99),
+                    degenerated_to_sgd=True)
+        opt.grad_scale = sync.grad_scale
+        opt.step()
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        other = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(other, flat)
+        assert all(torch.equal(o, other[0]) for o in other), "ranks diverged after the optimizer step"
+        q.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dp_gradient_equivalence_two_gpus():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results

@@ -517,6 +517,7 @@ def test_grad_sink_accumulation_semantics():
     x1 = g32(cases.points_in_box(3000, cases.BBOX_ODD, 1))
     x2 = g32(cases.points_in_box(5000, cases.BBOX_ODD, 2))
     dy1, dy2 = torch.randn(3000, 32, device=DEV), torch.randn(5000, 32, device=DEV)
+    ATOL = 1e-4  # atomically accumulated sums of O(10) values
 
     def reference(parts):
         ref, _ = make_embedder(cases.BBOX_ODD, 10)
@@ -547,11 +548,11 @@ def test_grad_sink_accumulation_semantics():
     opt.zero_grad()                                   # set_to_none=True
     assert all(e.weight.grad is None for e in emb.embeddings)
     (emb(x1)[0] * dy1).sum().backward()
-    close(torch.stack([e.weight.grad for e in emb.embeddings]), reference([(x1, dy1)]), GRAD_RTOL, atol=1e-9)
+    close(torch.stack([e.weight.grad for e in emb.embeddings]), reference([(x1, dy1)]), GRAD_RTOL, atol=ATOL)
 
     opt.zero_grad(set_to_none=False)                  # in-place zeroing of our slices
     (emb(x2)[0] * dy2).sum().backward()
-    close(torch.stack([e.weight.grad for e in emb.embeddings]), reference([(x2, dy2)]), GRAD_RTOL, atol=1e-9)
+    close(torch.stack([e.weight.grad for e in emb.embeddings]), reference([(x2, dy2)]), GRAD_RTOL, atol=ATOL)
 
     # a gradient that arrives through nn.Embedding first (as the TV loss does) is merged, not lost
     opt.zero_grad()
@@ -560,10 +561,10 @@ def test_grad_sink_accumulation_semantics():
     (emb(x1)[0] * dy1).sum().backward()
     want = reference([(x1, dy1)])
     want[3, :64] += 1.0
-    close(torch.stack([e.weight.grad for e in emb.embeddings]), want, GRAD_RTOL, atol=1e-9)
+    close(torch.stack([e.weight.grad for e in emb.embeddings]), want, GRAD_RTOL, atol=ATOL)
     emb.embeddings[3](idx).sum().backward()           # ... and after: autograd adds in place into our slice
     want[3, :64] += 1.0
-    close(torch.stack([e.weight.grad for e in emb.embeddings]), want, GRAD_RTOL, atol=1e-9)
+    close(torch.stack([e.weight.grad for e in emb.embeddings]), want, GRAD_RTOL, atol=ATOL)
     assert emb.embeddings[3].weight.grad.data_ptr() == emb._sink.flat[3 * 2048:].data_ptr()
 
 
