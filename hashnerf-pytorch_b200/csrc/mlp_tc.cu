@@ -49,21 +49,21 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ w, float
   stage_matrix(w + kG4, 3, 64, 8, 64, hi + oW4, lo + oW4);
 }
 
-// One layer: D = A . W^T as 3 x (K/8) MMAs; small terms first.  Called by ONE thread.
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t w_hi_saddr, uint32_t w_lo_saddr, int N, int K) {
-  const uint32_t idesc = make_idesc(kTile, N);
-  const uint32_t lbo = 128, sbo = (uint32_t)(K / 4) * 128;
-  uint32_t acc = 0;
-#pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t a = tmem + (pass == 0 ? kColAlo : kColAhi);
-    const uint32_t w = (pass == 1) ? w_lo_saddr : w_hi_saddr;
-#pragma unroll 1
-    for (int s = 0; s < K / 8; ++s) {
-      umma_ts(tmem + kColD, a + 8 * s, make_sdesc(w + s * 256, lbo, sbo), idesc, acc);
-      acc = 1;
-    }
-  }
+// One layer: D = A . W^T as 3 x (K/8) MMAs; small terms first.  Called by ONE thread: its instruction stream is
+// on the critical path of every layer, so N and K are template parameters (descriptor constants fold, the loops
+// unroll and a K step is one 64-bit add of 16 = 256 bytes >> 4 on the descriptor).
+template <int N, int K>
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t w_hi_saddr, uint32_t w_lo_saddr) {
+  constexpr uint32_t idesc = make_idesc(kTile, N);
+  constexpr uint64_t kHiBits = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(((K / 4) * 128) >> 4) << 32) | (1ull << 46);
+  const uint64_t d_hi = kHiBits | (uint64_t)((w_hi_saddr >> 4) & 0x3FFF);
+  const uint64_t d_lo = kHiBits | (uint64_t)((w_lo_saddr >> 4) & 0x3FFF);
+#pragma unroll
+  for (int s = 0; s < K / 8; ++s) umma_ts(tmem + kColD, tmem + kColAlo + 8 * s, d_hi + 16 * s, idesc, s ? 1u : 0u);
+#pragma unroll
+  for (int s = 0; s < K / 8; ++s) umma_ts(tmem + kColD, tmem + kColAhi + 8 * s, d_lo + 16 * s, idesc, 1u);
+#pragma unroll
+  for (int s = 0; s < K / 8; ++s) umma_ts(tmem + kColD, tmem + kColAhi + 8 * s, d_hi + 16 * s, idesc, 1u);
 }
 
 // write 16 activations (columns c0 .. c0+15 of this thread's row) as the next layer's A operand
@@ -83,14 +83,15 @@ __device__ __forceinline__ void ctx_sync(int sync_id) {
   else asm volatile("bar.sync %0, %1;" ::"r"(sync_id), "r"(kTile) : "memory");
 }
 
+template <int N, int K>
 __device__ __forceinline__ void run_layer(uint32_t tmem, uint64_t* bar, uint32_t& phase, uint32_t w_hi, uint32_t w_lo,
-                                          int N, int K, int sync_id = 0, bool leader = (threadIdx.x == 0)) {
+                                          int sync_id = 0, bool leader = (threadIdx.x == 0)) {
   wait_st();
   fence_before_sync();
   ctx_sync(sync_id);
   if (leader) {
     fence_after_sync();
-    issue_layer(tmem, w_hi, w_lo, N, K);
+    issue_layer<N, K>(tmem, w_hi, w_lo);
     umma_commit(bar);
   }
   mbar_wait(bar, phase);
@@ -151,7 +152,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
         put16(row, c0, v);
       }
     }
-    run_layer(tmem, &bar, phase, s_hi + oW0 * 4, s_lo + oW0 * 4, 64, 32);  // h1 pre-activation
+    run_layer<64, 32>(tmem, &bar, phase, s_hi + oW0 * 4, s_lo + oW0 * 4);  // h1 pre-activation
 #pragma unroll
     for (int c0 = 0; c0 < kHid; c0 += 16) {
       float v[16];
@@ -161,7 +162,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       put16(row, c0, v);
     }
     fence_before_sync();  // D has been read: the next MMA may overwrite it after the barrier
-    run_layer(tmem, &bar, phase, s_hi + oW1 * 4, s_lo + oW1 * 4, 16, 64);  // h2 = [sigma | geo]
+    run_layer<16, 64>(tmem, &bar, phase, s_hi + oW1 * 4, s_lo + oW1 * 4);  // h2 = [sigma | geo]
     float sigma;
     {
       float h2[16];
@@ -179,7 +180,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       put16(row, 16, v);
     }
     fence_before_sync();
-    run_layer(tmem, &bar, phase, s_hi + oW2 * 4, s_lo + oW2 * 4, 64, 32);  // h3
+    run_layer<64, 32>(tmem, &bar, phase, s_hi + oW2 * 4, s_lo + oW2 * 4);  // h3
 #pragma unroll
     for (int c0 = 0; c0 < kHid; c0 += 16) {
       float v[16];
@@ -189,7 +190,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       put16(row, c0, v);
     }
     fence_before_sync();
-    run_layer(tmem, &bar, phase, s_hi + oW3 * 4, s_lo + oW3 * 4, 64, 64);  // h4
+    run_layer<64, 64>(tmem, &bar, phase, s_hi + oW3 * 4, s_lo + oW3 * 4);  // h4
 #pragma unroll
     for (int c0 = 0; c0 < kHid; c0 += 16) {
       float v[16];
@@ -199,7 +200,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       put16(row, c0, v);
     }
     fence_before_sync();
-    run_layer(tmem, &bar, phase, s_hi + oW4 * 4, s_lo + oW4 * 4, 8, 64);  // rgb (N padded to 8)
+    run_layer<8, 64>(tmem, &bar, phase, s_hi + oW4 * 4, s_lo + oW4 * 4);  // rgb (N padded to 8)
     {
       float rgb[8];
       tmem_ld8(row + kColD, rgb);
@@ -354,10 +355,10 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
     for (int i = 3; i < 8; ++i) g[(rDrgb + i) * kTile] = 0.f;
 
     // ---- forward recompute
-    run_layer(tmem, bar_p, phase, s_hi + oW0 * 4, s_lo + oW0 * 4, 64, 32, sync_id, leader);
+    run_layer<64, 32>(tmem, bar_p, phase, s_hi + oW0 * 4, s_lo + oW0 * 4, sync_id, leader);
     const uint64_t m1 = epilogue64<true>(row, g + rH1 * kTile, 0, false);
     fence_before_sync();
-    run_layer(tmem, bar_p, phase, s_hi + oW1 * 4, s_lo + oW1 * 4, 16, 64, sync_id, leader);
+    run_layer<16, 64>(tmem, bar_p, phase, s_hi + oW1 * 4, s_lo + oW1 * 4, sync_id, leader);
     {
       float h2[16];
       tmem_ld16(row + kColD, h2);
@@ -377,10 +378,10 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
       put16(row, 16, v);
     }
     fence_before_sync();
-    run_layer(tmem, bar_p, phase, s_hi + oW2 * 4, s_lo + oW2 * 4, 64, 32, sync_id, leader);
+    run_layer<64, 32>(tmem, bar_p, phase, s_hi + oW2 * 4, s_lo + oW2 * 4, sync_id, leader);
     const uint64_t m3 = epilogue64<true>(row, g + rH3 * kTile, 0, false);
     fence_before_sync();
-    run_layer(tmem, bar_p, phase, s_hi + oW3 * 4, s_lo + oW3 * 4, 64, 64, sync_id, leader);
+    run_layer<64, 64>(tmem, bar_p, phase, s_hi + oW3 * 4, s_lo + oW3 * 4, sync_id, leader);
     uint64_t m4 = 0;
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 16) {  // h4: only its values (for dW4) and its mask are needed
@@ -403,13 +404,13 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
       put16(row, 0, v);  // A = drgb, K = 8 (columns 3..7 zero)
     }
     fence_before_sync();
-    run_layer(tmem, bar_p, phase, s_hi + oT4 * 4, s_lo + oT4 * 4, 64, 8, sync_id, leader);    // dh4 = drgb . W4
+    run_layer<64, 8>(tmem, bar_p, phase, s_hi + oT4 * 4, s_lo + oT4 * 4, sync_id, leader);    // dh4 = drgb . W4
     epilogue64<false>(row, g + rDz4 * kTile, m4, true);                      // dz4 = dh4 . [h4 > 0]
     fence_before_sync();
-    run_layer(tmem, bar_p, phase, s_hi + oT3 * 4, s_lo + oT3 * 4, 64, 64, sync_id, leader);   // dh3 = dz4 . W3
+    run_layer<64, 64>(tmem, bar_p, phase, s_hi + oT3 * 4, s_lo + oT3 * 4, sync_id, leader);   // dh3 = dz4 . W3
     epilogue64<false>(row, g + rDz3 * kTile, m3, true);                      // dz3
     fence_before_sync();
-    run_layer(tmem, bar_p, phase, s_hi + oT2 * 4, s_lo + oT2 * 4, 16, 64, sync_id, leader);   // dgeo = (dz3 . W2)[16:31]
+    run_layer<16, 64>(tmem, bar_p, phase, s_hi + oT2 * 4, s_lo + oT2 * 4, sync_id, leader);   // dgeo = (dz3 . W2)[16:31]
     {
       float dg[16], v[16];
       tmem_ld16(row + kColD, dg);
@@ -421,10 +422,10 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
       put16(row, 0, v);  // A = dh2, K = 16
     }
     fence_before_sync();
-    run_layer(tmem, bar_p, phase, s_hi + oT1 * 4, s_lo + oT1 * 4, 64, 16, sync_id, leader);   // dh1 = dh2 . W1
+    run_layer<64, 16>(tmem, bar_p, phase, s_hi + oT1 * 4, s_lo + oT1 * 4, sync_id, leader);   // dh1 = dh2 . W1
     epilogue64<false>(row, g + rDz1 * kTile, m1, true);                      // dz1
     fence_before_sync();
-    run_layer(tmem, bar_p, phase, s_hi + oT0 * 4, s_lo + oT0 * 4, 32, 64, sync_id, leader);   // d_enc = dz1 . W0
+    run_layer<32, 64>(tmem, bar_p, phase, s_hi + oT0 * 4, s_lo + oT0 * 4, sync_id, leader);   // d_enc = dz1 . W0
 #pragma unroll
     for (int c0 = 0; c0 < kIn; c0 += 16) {
       float v[16];
@@ -452,13 +453,14 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 // ================================================================================================
 constexpr int kHalf = 64;
 constexpr uint32_t cW0 = 0, cW1 = 32, cW2 = 48, cW3 = 80, cW4 = 144;  // accumulator columns
-constexpr size_t kWeightSmemBytes = (size_t)4 * 64 * kHalf * sizeof(float);  // M_hi | M_lo | N_hi | N_lo  (64 KB)
+constexpr size_t kWeightSmemBytes = (size_t)2 * 4 * 64 * kHalf * sizeof(float);  // 2 x (M_hi | M_lo | N_hi | N_lo) = 128 KB
 
 // Staging of one operand pair for a 64-point half tile.  Slot s of thread t covers float4 number s*128 + t of
 // the pair: the first 1024 belong to the 64 M-side rows, the rest to the N-side rows.  Within an operand,
 // consecutive indices walk (row % 8, 16-byte chunk, row group) so that the 8 lanes of one chunk fill one
 // 128-byte core matrix (conflict-free STS.128) while reading 64 contiguous bytes per row.
-constexpr int kSlots = 16;  // (64 + 64 rows) * 16 chunks / 128 threads
+constexpr int kWThreads = 256;  // threads of the weight-gradient kernel
+constexpr int kSlots = 8;    // (64 + 64 rows) * 16 chunks / 256 threads
 
 struct PairDesc {
   int m_row, n_row, n_rows;
@@ -469,7 +471,7 @@ __device__ __forceinline__ void prefetch_pair(const float* __restrict__ base, co
   const int total = (64 + pr.n_rows) * (kHalf / 4);
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) {
-    const int idx = s * kTile + threadIdx.x;
+    const int idx = s * kWThreads + threadIdx.x;
     reg[s] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (idx < total) {
       const bool is_n = idx >= 64 * (kHalf / 4);
@@ -487,7 +489,7 @@ __device__ __forceinline__ void store_pair(const PairDesc& pr, const float4 (&re
   const int total = (64 + pr.n_rows) * (kHalf / 4);
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) {
-    const int idx = s * kTile + threadIdx.x;
+    const int idx = s * kWThreads + threadIdx.x;
     if (idx < total) {
       const bool is_n = idx >= 64 * (kHalf / 4);
       const int i = is_n ? idx - 64 * (kHalf / 4) : idx;
@@ -505,18 +507,17 @@ __device__ __forceinline__ void store_pair(const PairDesc& pr, const float4 (&re
   }
 }
 
-__global__ void __launch_bounds__(kTile, 2)
+// 256 threads, one CTA per SM, two staging buffers: while the tensor core consumes pair q from buffer q & 1 the
+// threads split and store pair q + 1 into the other buffer and the global loads of pair q + 2 are in flight.
+__global__ void __launch_bounds__(kWThreads, 1)
 mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restrict__ dweights) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  float* Mhi = smem;
-  float* Mlo = Mhi + 64 * kHalf;
-  float* Nhi = Mlo + 64 * kHalf;
-  float* Nlo = Nhi + 64 * kHalf;
   if (t == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
@@ -524,70 +525,87 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  uint32_t phase = 0;
-  bool pending = false;   // an MMA group reading the staging buffers is in flight
-  uint32_t fresh = 0x1f;  // bit i set: accumulator i has not been written yet (first MMA overwrites)
+  uint32_t phase[2] = {0u, 0u};
+  bool used[2] = {false, false};  // an MMA group reading this staging buffer has been committed
+  uint32_t fresh = 0x1f;          // bit i set: accumulator i has not been written yet (first MMA overwrites)
 
   // (M-side rows, N-side rows): dW0 = dz1^T.in, dW1^T = h1^T.dh2, dW2 = dz3^T.c, dW3 = dz4^T.h3, dW4^T = h4^T.drgb
   const PairDesc pairs[5] = {{rDz1, rIn, 32, cW0}, {rH1, rDh2, 16, cW1}, {rDz3, rC, 32, cW2}, {rDz4, rH3, 64, cW3},
                              {rH4, rDrgb, 8, cW4}};
   const int64_t n_half = ((N + kTile - 1) / kTile) * 2;
-  const int64_t my_first = blockIdx.x;
-  float4 reg[kSlots];
-  if (my_first < n_half)
-    prefetch_pair(ws + (my_first >> 1) * (int64_t)(kWsRowsTc * kTile) + (my_first & 1) * kHalf, pairs[0], reg);
-  for (int64_t h = my_first; h < n_half; h += gridDim.x) {
-    const float* base = ws + (h >> 1) * (int64_t)(kWsRowsTc * kTile) + (h & 1) * kHalf;
+  const int64_t G = gridDim.x;
+  auto base_of = [&](int64_t hh) { return ws + (hh >> 1) * (int64_t)(kWsRowsTc * kTile) + (hh & 1) * kHalf; };
+  // Two register sets: the set consumed at step k is refilled at once with the loads of step k + 2, so global
+  // loads have two full pair-times (several microseconds) to land.  A loop iteration covers two half tiles
+  // = 10 steps, which keeps the set <-> step mapping static.
+  float4 ra[kSlots], rb[kSlots];
+  int64_t h = blockIdx.x;
+  if (h < n_half) {
+    prefetch_pair(base_of(h), pairs[0], ra);
+    prefetch_pair(base_of(h), pairs[1], rb);
+  }
+  int q = 0;
+  for (; h < n_half; h += 2 * G) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int k = 0; k < 10; ++k) {
+      const int64_t hh = h + (k / 5) * G;
+      if (hh >= n_half) break;
+      const int i = k % 5;
+      float4(&cur)[kSlots] = (k & 1) ? rb : ra;
       const PairDesc pr = pairs[i];
-      if (pending) {  // the previous MMAs must have consumed the staging buffers
-        mbar_wait(&bar, phase);
-        phase ^= 1u;
-        pending = false;
+      const int b = q & 1;
+      ++q;
+      float* Mhi = smem + b * (4 * 64 * kHalf);
+      float* Mlo = Mhi + 64 * kHalf;
+      float* Nhi = Mlo + 64 * kHalf;
+      float* Nlo = Nhi + 64 * kHalf;
+      if (used[b]) {  // the MMAs issued two steps ago must have consumed this buffer
+        mbar_wait(&bars[b], phase[b]);
+        phase[b] ^= 1u;
       }
-      store_pair(pr, reg, Mhi, Mlo, Nhi, Nlo);
+      store_pair(pr, cur, Mhi, Mlo, Nhi, Nlo);
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
       if (t == 0) {
         fence_after_sync();
         const uint32_t idesc = make_idesc(64, pr.n_rows);
-        const uint32_t lbo = 128, sbo = (kHalf / 4) * 128;
-        uint32_t acc = ((fresh >> i) & 1u) ? 0u : 1u;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a = smem_u32(pass == 0 ? Mlo : Mhi);
-          const uint32_t b = smem_u32(pass == 1 ? Nlo : Nhi);
-#pragma unroll 1
-          for (int s = 0; s < kHalf / 8; ++s) {
-            umma_ss(tmem + pr.col, make_sdesc(a + s * 256, lbo, sbo), make_sdesc(b + s * 256, lbo, sbo), idesc, acc);
-            acc = 1;
-          }
-        }
-        umma_commit(&bar);
+        constexpr uint64_t kHiBits =
+            ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(((kHalf / 4) * 128) >> 4) << 32) | (1ull << 46);
+        const uint64_t m_hi = kHiBits | (uint64_t)((smem_u32(Mhi) >> 4) & 0x3FFF);
+        const uint64_t m_lo = kHiBits | (uint64_t)((smem_u32(Mlo) >> 4) & 0x3FFF);
+        const uint64_t n_hi = kHiBits | (uint64_t)((smem_u32(Nhi) >> 4) & 0x3FFF);
+        const uint64_t n_lo = kHiBits | (uint64_t)((smem_u32(Nlo) >> 4) & 0x3FFF);
+        const uint32_t first = ((fresh >> i) & 1u) ? 0u : 1u;
+        const uint32_t d = tmem + pr.col;
+#pragma unroll
+        for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_lo + 16 * s, n_hi + 16 * s, idesc, s ? 1u : first);
+#pragma unroll
+        for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_hi + 16 * s, n_lo + 16 * s, idesc, 1u);
+#pragma unroll
+        for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_hi + 16 * s, n_hi + 16 * s, idesc, 1u);
+        umma_commit(&bars[b]);
       }
       fresh &= ~(1u << i);
-      pending = true;
-      // global loads of the next pair fly while the tensor core works on this one
-      if (i < 4) {
-        prefetch_pair(base, pairs[i + 1], reg);
-      } else if (h + gridDim.x < n_half) {
-        const int64_t hn = h + gridDim.x;
-        prefetch_pair(ws + (hn >> 1) * (int64_t)(kWsRowsTc * kTile) + (hn & 1) * kHalf, pairs[0], reg);
-      }
+      used[b] = true;
+      // refill this register set with step k + 2
+      const int k2 = k + 2;
+      const int64_t h2 = (k2 < 10) ? h + (k2 / 5) * G : h + 2 * G;
+      if (h2 < n_half) prefetch_pair(base_of(h2), pairs[k2 % 5], cur);
     }
   }
-  if (pending) {
-    mbar_wait(&bar, phase);
-    phase ^= 1u;
-  }
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+    if (used[b]) {
+      mbar_wait(&bars[b], phase[b]);
+      phase[b] ^= 1u;
+    }
   fence_after_sync();
   // ---- flush: M = 64 accumulators keep row m in lane (m % 16) + 32 * (m / 16)
   const bool any = blockIdx.x < n_half;
-  const int m = warp * 16 + lane;  // valid for lane < 16
-  const uint32_t row = tmem + ((uint32_t)(warp * 32) << 16);
-  if (any) {
+  const int m = warp * 16 + lane;  // valid for lane < 16, warps 0..3 (each warp reads its own 32-lane quadrant)
+  const uint32_t row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  if (any && warp < 4) {
     float v[16];
     // dW0[j = m][k]   (64 x 32)
 #pragma unroll
@@ -687,9 +705,9 @@ int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   }
   {
     const int64_t halves = tiles * 2;
-    const int64_t cap = (int64_t)sm_count() * 2;
+    const int64_t cap = (int64_t)sm_count();
     const unsigned grid = (unsigned)(halves < cap ? halves : cap);
-    tc::mlp_tc_bwd_weight_kernel<<<grid, tc::kTile, tc::kWeightSmemBytes, stream>>>(N, workspace, dweights);
+    tc::mlp_tc_bwd_weight_kernel<<<grid, tc::kWThreads, tc::kWeightSmemBytes, stream>>>(N, workspace, dweights);
     return check_launch("mlp_tc_bwd_weight_kernel");
   }
 }

@@ -122,15 +122,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
-// ---- 3xTF32 split: a = hi + lo with hi, lo on the tf32 grid (round-to-nearest) ---------------------------
-__device__ __forceinline__ uint32_t to_tf32(float a) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
-  return r;
-}
+// ---- 3xTF32 split: a = hi + lo, hi on the tf32 grid (round to nearest), lo = a - hi exact in fp32 ------------
+// The tensor core ignores the 13 low mantissa bits of a tf32 operand, so hi must be rounded here (integer add of
+// half an ulp, then mask: 2 instructions -- cvt.rna.tf32.f32 expands to ~5 with its NaN/Inf handling, which this
+// data never needs) while lo can be handed over unrounded: the hardware's truncation of lo costs <= 2^-21 |a|.
+__device__ __forceinline__ uint32_t to_tf32(float a) { return (__float_as_uint(a) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32(a);
-  lo = to_tf32(a - __uint_as_float(hi));
+  lo = __float_as_uint(a - __uint_as_float(hi));
 }
 
 }  // namespace tc

@@ -45,8 +45,11 @@ SIGNATURES = {
     "hn_radam_step": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _i, _f, _p]),
 }
 
+# kernels launched per entry point (1 unless listed): hn_hash_sort_points = hist + 3 scan kernels + scatter
+KERNELS_PER_CALL = {"hn_hash_sort_points": 5, "hn_mlp_bwd": 2}
+
 _lib = None
-launches = 0  # number of kernel-launching C-ABI calls made through call() (bench.py reports it)
+launches = 0  # number of CUDA kernels launched through call() (bench.py reports it as gpu_launches)
 
 
 def load() -> C.CDLL:
@@ -76,7 +79,7 @@ def call(name: str, *args) -> None:
     if rc != 0:
         msg = lib.hn_last_error_string().decode("utf-8", "replace")
         raise RuntimeError(f"{name} failed with status {rc}: {msg}")
-    launches += 1
+    launches += KERNELS_PER_CALL.get(name, 1)
 
 
 def set_tuning(key: str, value: int) -> None:

@@ -11,5 +11,11 @@ steps = int(os.environ.get("STEPS", 3))
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 graphed = bool(int(os.environ.get("GRAPH", 0)))
+from hn_b200 import _lib, ops
+if "SORT_MIN" in os.environ:
+    ops.SORT_MIN_POINTS = int(os.environ["SORT_MIN"])
+for knob in ("hash_bwd_agg", "hash_fwd_lpg", "hash_bwd_lpg", "hash_agg_max_heads", "mlp_impl"):
+    if knob.upper() in os.environ:
+        _lib.set_tuning(knob, int(os.environ[knob.upper()]))
 rps, ms = bench.train_step_extra(dev, n_rand, steps=steps, warmup=int(os.environ.get("WARMUP", 2)), graphed=graphed)
 print(json.dumps({"n_rand": n_rand, "graphed": graphed, "ms_per_step": round(ms, 3), "rays_per_s": round(rps, 1)}))
