@@ -9,6 +9,8 @@ CUDA only; a CPU tensor raises RuntimeError.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -67,6 +69,11 @@ class HashEmbedder(nn.Module):
             nn.init.uniform_(emb.weight, a=-0.0001, b=0.0001)
         self._flatten_parameters()
         self._geom_cache = {}
+        # let code that is handed a single level (loss.total_variation_loss gets embeddings[i]) find its way back
+        # to the shared gradient buffer
+        for l, emb in enumerate(self.embeddings):
+            object.__setattr__(emb, "_hn_owner", weakref.ref(self))
+            object.__setattr__(emb, "_hn_level", l)
         # None: re-order large batches by grid cell before encoding (results unchanged, see ops.HashEncodeFn);
         # True / False force the choice.
         self.coherent = None
@@ -127,17 +134,21 @@ class HashEmbedder(nn.Module):
         feats, keep = self.encode(x)
         return feats, keep.bool()
 
+    def grad_sink(self):
+        """The persistent flat gradient buffer manager of the level tables (None if disabled)."""
+        if not self.fused_grad_accumulation:
+            return None
+        if self._sink is None or any(a is not b for a, b in zip(self._sink.params, self._level_weights())):
+            self._sink = ops.GradSink(self._level_weights())
+        return self._sink
+
     def encode(self, x):
         """Same as forward() but the mask stays the kernel's uint8 (what the fused MLP consumes)."""
         lead = x.shape[:-1]
         pts = x.reshape(-1, 3)
         box, res = self._geometry(pts.device)
         self._flatten_parameters()
-        sink = None
-        if self.fused_grad_accumulation and torch.is_grad_enabled():
-            if self._sink is None or any(a is not b for a, b in zip(self._sink.params, self._level_weights())):
-                self._sink = ops.GradSink(self._level_weights())
-            sink = self._sink
+        sink = self.grad_sink() if torch.is_grad_enabled() else None
         feats, keep = ops.HashEncodeFn.apply(pts, box, res, self.log2_hashmap_size, self.n_features_per_level,
                                              self.coherent, sink, *self._level_weights())
         if len(lead) != 1:

@@ -281,6 +281,44 @@ class HashEncodeFn(torch.autograd.Function):
         return (None, None, None, None, None, None, None) + tuple(grads)
 
 
+class TVLossFn(torch.autograd.Function):
+    """tv = TVLossFn.apply(weight [2^T, F], origin int64[3] (device), cube, log2T, sink_info|None)
+
+    ``sink_info`` = (GradSink, element offset of this level in its flat buffer): the backward kernel then
+    scatters straight into the persistent gradient buffer; otherwise a dense gradient is returned."""
+
+    @staticmethod
+    def forward(ctx, weight, origin, cube, log2T, sink_info):
+        dev = _need_cuda(weight, origin)
+        w = weight.detach()
+        if not w.is_contiguous() or w.dtype != torch.float32:
+            raise RuntimeError("TV loss expects a contiguous fp32 table")
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with _on(dev):
+            _lib.call("hn_tv_loss_fwd", w.data_ptr(), origin.data_ptr(), int(cube), int(log2T), int(w.shape[1]),
+                      out.data_ptr(), _stream())
+        ctx.save_for_backward(w, origin)
+        ctx.meta = (int(cube), int(log2T), sink_info)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        w, origin = ctx.saved_tensors
+        cube, log2T, sink_info = ctx.meta
+        gout = _f32c(gout)
+        if sink_info is not None:
+            sink, offset = sink_info
+            target = sink.acquire()[offset:offset + w.numel()]
+            ret = None
+        else:
+            target = torch.zeros_like(w)
+            ret = target
+        with _on(w.device):
+            _lib.call("hn_tv_loss_bwd", w.data_ptr(), origin.data_ptr(), cube, log2T, int(w.shape[1]),
+                      gout.data_ptr(), target.data_ptr(), _stream())
+        return ret, None, None, None, None
+
+
 # ----------------------------------------------------------------------------------------------
 # spherical harmonics
 # ----------------------------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 """Regularisers -- drop-in for the reference's ``loss.py`` (total_variation_loss :11-43,
-sigma_sparsity_loss :45-47).  Adjacent to the hot path ("next" row 2): the hashed
-gather uses the CUDA spatial hash; the finite differences stay in PyTorch for now.
+sigma_sparsity_loss :45-47).  Adjacent to the hot path ("next" row 2): one CUDA launch for
+the forward (hash, gather, squared differences, reduction) and one for the backward, instead of ~15 ATen
+launches per level.
 """
 from __future__ import annotations
 
@@ -8,7 +9,8 @@ from math import exp, floor, log
 
 import torch
 
-from embedding.hash_encoding import hash
+from embedding.hash_encoding import hash  # noqa: F401  (reference import line loss.py:8)
+from hn_b200 import ops
 
 
 def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2_hashmap_size, n_levels=16):
@@ -24,15 +26,16 @@ def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2
         raise ValueError("ALERT! min cuboid size greater than max!")  # the reference drops into pdb here
     cube = int(floor(min(max(resolution / 10.0, smallest), largest)))
 
-    dev = embeddings.weight.device
-    origin = torch.randint(0, resolution - cube, (3,)).to(dev)  # drawn like loss.py:25, then moved
-    ax = torch.arange(cube + 1, device=dev)
-    gx, gy, gz = torch.meshgrid(origin[0] + ax, origin[1] + ax, origin[2] + ax, indexing="ij")
-    feats = embeddings(hash(torch.stack([gx, gy, gz], dim=-1), log2_hashmap_size))
-    tv = torch.pow(feats[1:] - feats[:-1], 2).sum() \
-        + torch.pow(feats[:, 1:] - feats[:, :-1], 2).sum() \
-        + torch.pow(feats[:, :, 1:] - feats[:, :, :-1], 2).sum()
-    return tv / cube
+    weight = embeddings.weight
+    origin = torch.randint(0, resolution - cube, (3,)).to(weight.device)  # drawn like loss.py:25, then moved
+    sink_info = None
+    owner = getattr(embeddings, "_hn_owner", None)
+    owner = owner() if owner is not None else None
+    if owner is not None and torch.is_grad_enabled() and weight.requires_grad:
+        sink = owner.grad_sink()
+        if sink is not None:
+            sink_info = (sink, embeddings._hn_level * weight.numel())
+    return ops.TVLossFn.apply(weight, origin, cube, log2_hashmap_size, sink_info)
 
 
 def sigma_sparsity_loss(sigmas):

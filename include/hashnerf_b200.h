@@ -154,6 +154,15 @@ HN_API int hn_radam_step(float* p, const float* g, float* m, float* v, int64_t n
                          float eps, float lr, float weight_decay, float step_size, int mode, float grad_scale,
                          void* stream);
 
+/* ---- section 8f "next" row 2: total_variation_loss : loss.py:11-43 ---------------------------------- */
+/* One hash level: table [2^log2T, F]; origin = int64[3] on the device (the random cube corner drawn at
+ * loss.py:25); cube = cube size (loss.py:22).  fwd writes out[0] = (sum of squared forward differences over the
+ * (cube+1)^3 hashed vertices) / cube.  bwd ACCUMULATES gout[0] * d out / d table into dtable [2^log2T, F]. */
+HN_API int hn_tv_loss_fwd(const float* table, const int64_t* origin, int cube, int log2T, int F, float* out,
+                          void* stream);
+HN_API int hn_tv_loss_bwd(const float* table, const int64_t* origin, int cube, int log2T, int F, const float* gout,
+                          float* dtable, void* stream);
+
 /* CUDA-graph friendly form: the step-dependent scalars come from device memory,
  * hp = {beta1, beta2, eps, weight_decay*lr, step_size*lr, grad_scale, mode, unused}. */
 HN_API int hn_radam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hp, void* stream);
