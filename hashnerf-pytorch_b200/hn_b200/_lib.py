@@ -41,6 +41,8 @@ SIGNATURES = {
     "hn_sort_concat_rows": (_i, [_p, _i, _p, _i, _l, _p, _p]),
     "hn_coarse_z": (_i, [_p, _p, _l, _p, _p, _l, _i, _i, _p, _p]),
     "hn_ray_points": (_i, [_p, _p, _l, _p, _l, _i, _p, _p]),
+    "hn_get_rays": (_i, [_i, _i, _f, _f, _f, _f, _p, _l, _p, _p]),
+    "hn_pack_rays": (_i, [_p, _l, _p, _l, _p, _l, _f, _f, _l, _p, _p]),
     "hn_tv_loss_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "hn_tv_loss_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "hn_radam_step_dev": (_i, [_p, _p, _p, _p, _l, _p, _p]),

@@ -199,40 +199,42 @@ class GradSink:
     def __init__(self, params):
         self.params = list(params)
         self.flat = None
+        self._views = None  # one view of `flat` per parameter, created once (param.grad is set to these objects)
 
-    def _slices(self):
-        out, off = [], 0
+    def _allocate(self):
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._views, off = [], 0
         for p in self.params:
-            out.append(self.flat[off:off + p.numel()].view_as(p))
+            self._views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
-        return out
 
     def acquire(self) -> torch.Tensor:
         """Flat fp32 buffer to accumulate into; afterwards every param.grad is a slice of it."""
-        dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        if self.flat is None or self.flat.device != dev or self.flat.numel() != n:
-            self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        fresh = False
+        if self.flat is None or self.flat.device != self.params[0].device:
+            self._allocate()
             fresh = True
-        else:
-            fresh = False
-        slices = self._slices()
-        mine = [p.grad is not None and p.grad.data_ptr() == s.data_ptr() and p.grad.shape == s.shape
-                for p, s in zip(self.params, slices)]
+        views = self._views
+        mine = [p.grad is v for p, v in zip(self.params, views)]
         if all(mine):
-            return self.flat                      # still accumulating into our buffer
-        foreign = [(s, p.grad) for p, s, m in zip(self.params, slices, mine) if (not m) and p.grad is not None]
+            return self.flat                      # still accumulating into our buffer (the common case)
+        for i, (p, v) in enumerate(zip(self.params, views)):   # same memory through another tensor object
+            if not mine[i] and p.grad is not None and p.grad.data_ptr() == v.data_ptr() and p.grad.shape == v.shape:
+                mine[i] = True
+        foreign = [(v, p.grad) for p, v, m in zip(self.params, views, mine) if (not m) and p.grad is not None]
         if not fresh:
             if any(mine):                         # mixed state: keep what is ours, clear the rest
-                for p, s, m in zip(self.params, slices, mine):
+                for v, m in zip(views, mine):
                     if not m:
-                        s.zero_()
+                        v.zero_()
             else:
                 self.flat.zero_()                 # first backward since zero_grad(set_to_none=True)
-        for s, g in foreign:                      # gradients that arrived through plain autograd
-            s.add_(g)
-        for p, s in zip(self.params, slices):
-            p.grad = s
+        for v, g in foreign:                      # gradients that arrived through plain autograd
+            v.add_(g)
+        for p, v in zip(self.params, views):
+            p.grad = v
         return self.flat
 
 
@@ -503,3 +505,37 @@ def ray_points(rays_o, rays_d, ray_stride: int, z) -> torch.Tensor:
         _lib.call("hn_ray_points", rays_o.data_ptr(), rays_d.data_ptr(), int(ray_stride), z.data_ptr(), R, S,
                   pts.data_ptr(), _stream())
     return pts
+
+
+# ----------------------------------------------------------------------------------------------
+# ray generation / packing (no gradients: cameras are data)
+# ----------------------------------------------------------------------------------------------
+@torch.no_grad()
+def get_rays_d(H: int, W: int, fx: float, fy: float, cx: float, cy: float, c2w: torch.Tensor) -> torch.Tensor:
+    dev = _need_cuda(c2w)
+    m = c2w if (c2w.dtype == torch.float32 and c2w.stride(-1) == 1) else c2w.float().contiguous()
+    out = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_get_rays", int(H), int(W), float(fx), float(fy), float(cx), float(cy), m.data_ptr(),
+                  int(m.stride(0)), out.data_ptr(), _stream())
+    return out
+
+
+def _rows3(t: torch.Tensor):
+    if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+        t = t.float().contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else 3)
+
+
+@torch.no_grad()
+def pack_rays(rays_o, rays_d, viewdirs, near: float, far: float) -> torch.Tensor:
+    dev = _need_cuda(rays_o, rays_d, viewdirs)
+    o, so = _rows3(rays_o)
+    d, sd = _rows3(rays_d)
+    v, sv = (None, 0) if viewdirs is None else _rows3(viewdirs)
+    R = d.shape[0]
+    out = torch.empty(R, 11 if v is not None else 8, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_pack_rays", o.data_ptr(), so, d.data_ptr(), sd, _ptr(v), sv, float(near), float(far), R,
+                  out.data_ptr(), _stream())
+    return out

@@ -27,7 +27,11 @@ def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2
     cube = int(floor(min(max(resolution / 10.0, smallest), largest)))
 
     weight = embeddings.weight
-    origin = torch.randint(0, resolution - cube, (3,)).to(weight.device)  # drawn like loss.py:25, then moved
+    # loss.py:25 draws on the default device; the reference only works when that is the tables' device, so draw
+    # there directly (no host round trip)
+    origin = torch.randint(0, resolution - cube, (3,), device=weight.device)
+    if origin.device != weight.device:
+        origin = origin.to(weight.device)
     sink_info = None
     owner = getattr(embeddings, "_hn_owner", None)
     owner = owner() if owner is not None else None

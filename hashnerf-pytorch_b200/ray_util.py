@@ -1,8 +1,8 @@
 """Ray generation -- drop-in for the functions of the reference's ``ray_util.py`` that ``run_nerf.py`` and
 ``render`` use (get_rays :62-80, get_rays_np :82-93, get_ndc_rays :96-142).
 
-These feed the hot path but are not on it ("next" row 3): plain tensor math kept in
-PyTorch.  The kornia-based equirectangular helpers (ray_util.py:8-57) serve the st3d branch, which is
+These feed the hot path but are not on it ("next" row 3).  ``get_rays`` on a CUDA pose is one
+kernel launch (hn_get_rays); the numpy variant and the NDC warp stay plain array math.  The kornia-based equirectangular helpers (ray_util.py:8-57) serve the st3d branch, which is
 dead in the reference (Appendix B6), and are not provided.
 """
 from __future__ import annotations
@@ -13,6 +13,10 @@ import torch
 
 def get_rays(H, W, K, c2w):
     """Pinhole camera rays in world space: (rays_o, rays_d), each [H, W, 3]."""
+    if isinstance(c2w, torch.Tensor) and c2w.is_cuda:
+        from hn_b200 import ops
+        rays_d = ops.get_rays_d(H, W, K[0][0], K[1][1], K[0][2], K[1][2], c2w)
+        return c2w[:3, -1].expand(rays_d.shape), rays_d
     dev = c2w.device if isinstance(c2w, torch.Tensor) else None
     xs = torch.linspace(0, W - 1, W, device=dev)
     ys = torch.linspace(0, H - 1, H, device=dev)

@@ -317,19 +317,24 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
         viewdirs = rays_d
         if c2w_staticcam is not None:
             rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
-        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
-        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
 
     out_shape = rays_d.shape
     if ndc:
         rays_o, rays_d = get_ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
-    rays_o = torch.reshape(rays_o, [-1, 3]).float()
-    rays_d = torch.reshape(rays_d, [-1, 3]).float()
-    ones = torch.ones_like(rays_d[..., :1])
-    columns = [rays_o, rays_d, near * ones, far * ones]
-    if use_viewdirs:
-        columns.append(viewdirs)
-    packed = torch.cat(columns, -1)
+    rays_o = torch.reshape(rays_o, [-1, 3])
+    rays_d = torch.reshape(rays_d, [-1, 3])
+    if rays_d.is_cuda and isinstance(near, (int, float)) and isinstance(far, (int, float)):
+        # normalise the view directions and build [o | d | near | far | viewdir] in one launch
+        packed = ops.pack_rays(rays_o, rays_d, None if viewdirs is None else torch.reshape(viewdirs, [-1, 3]),
+                               near, far)
+    else:
+        rays_o, rays_d = rays_o.float(), rays_d.float()
+        ones = torch.ones_like(rays_d[..., :1])
+        columns = [rays_o, rays_d, near * ones, far * ones]
+        if use_viewdirs:
+            viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+            columns.append(torch.reshape(viewdirs, [-1, 3]).float())
+        packed = torch.cat(columns, -1)
 
     pieces = {}
     for i in range(0, packed.shape[0], chunk):

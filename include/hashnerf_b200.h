@@ -154,6 +154,17 @@ HN_API int hn_radam_step(float* p, const float* g, float* m, float* v, int64_t n
                          float eps, float lr, float weight_decay, float step_size, int mode, float grad_scale,
                          void* stream);
 
+/* ---- section 8f "next" row 3: ray generation / packing ------------------------------------------------- */
+/* ray_util.py:62-80: rays_d[H,W,3] for a pinhole camera (fx, fy, cx, cy) and a camera-to-world matrix c2w
+ * (3 rows of >= 3 floats, row stride in floats).  rays_o is the broadcast translation column: no kernel. */
+HN_API int hn_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w,
+                       int64_t c2w_row_stride, float* rays_d, void* stream);
+/* run_nerf_helpers.py:344-366: out[r] = (o, d, near, far[, viewdirs/|viewdirs|]); rows of o, d, viewdirs have
+ * the given strides (in floats); viewdirs may be NULL (row width 8 instead of 11). */
+HN_API int hn_pack_rays(const float* rays_o, int64_t o_stride, const float* rays_d, int64_t d_stride,
+                        const float* viewdirs, int64_t vd_stride, float near, float far, int64_t R, float* out,
+                        void* stream);
+
 /* ---- section 8f "next" row 2: total_variation_loss : loss.py:11-43 ---------------------------------- */
 /* One hash level: table [2^log2T, F]; origin = int64[3] on the device (the random cube corner drawn at
  * loss.py:25); cube = cube size (loss.py:22).  fwd writes out[0] = (sum of squared forward differences over the

@@ -469,6 +469,63 @@ def test_render_rays_golden(golden, name):
             mostly_close(lin.weight.grad, want, 1e-3, 1e-3 * np.abs(want).max(), 0.97, what=f"{tag} dW{i}")
 
 
+# ---------------------------------------------------------------------------------------------- rays / render
+def _pose(seed):
+    rs = np.random.RandomState(seed)
+    q, _ = np.linalg.qr(rs.randn(3, 3))
+    return np.concatenate([q, rs.randn(3, 1) * 2], -1).astype(np.float32)
+
+
+def test_get_rays_and_pack_rays():
+    from ray_util import get_rays
+    from hn_b200 import ops
+    H, W, focal = 37, 53, 61.5
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = _pose(3)
+    o_cpu, d_cpu = get_rays(H, W, K, t(c2w))                  # plain torch branch (CPU tensor)
+    o_gpu, d_gpu = get_rays(H, W, K, g32(c2w))                # hn_get_rays
+    assert d_gpu.shape == (H, W, 3) and o_gpu.shape == (H, W, 3)
+    close(d_gpu, d_cpu, 1e-6, atol=1e-6)
+    bit_equal(o_gpu.contiguous(), o_cpu.contiguous())
+    rays_o, rays_d = o_gpu.reshape(-1, 3), d_gpu.reshape(-1, 3)
+    packed = ops.pack_rays(rays_o, rays_d, rays_d, 2.0, 6.0)
+    assert packed.shape == (H * W, 11)
+    bit_equal(packed[:, 0:3].contiguous(), rays_o.contiguous())
+    bit_equal(packed[:, 3:6].contiguous(), rays_d.contiguous())
+    assert bool((packed[:, 6] == 2.0).all()) and bool((packed[:, 7] == 6.0).all())
+    close(packed[:, 8:], rays_d / torch.norm(rays_d, dim=-1, keepdim=True), 1e-6, atol=1e-7)
+    assert ops.pack_rays(rays_o, rays_d, None, 0.0, 1.0).shape == (H * W, 8)
+
+
+def test_render_full_image_against_oracle():
+    """render(c2w=...) -> get_rays -> pack -> chunked render_rays, coarse only, vs the oracle on the same rays."""
+    from embedding.spherical_harmonic import SHEncoder
+    from run_nerf_helpers import render, run_network
+    H, W, focal = 12, 10, 14.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = np.array([[1, 0, 0, 0.1], [0, 1, 0, -0.2], [0, 0, 1, 4.0]], np.float32)
+    emb, tables = make_embedder(cases.BBOX_UNIT, 12, scale=3000.0)
+    sig, col = cases.mlp_weights(5)
+    net = make_mlp(sig + col)
+    sh = SHEncoder()
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    with torch.no_grad():
+        rgb, depth, acc, extras = render(H, W, K, chunk=50, c2w=g32(c2w), ndc=False, near=2., far=6.,
+                                         use_viewdirs=True, network_fn=net, network_query_fn=qfn, N_samples=16,
+                                         embed_fn=emb, perturb=0., N_importance=0, white_bkgd=True)
+    assert rgb.shape == (H, W, 3) and depth.shape == (H, W) and "sparsity_loss" in extras
+    from ray_util import get_rays
+    o, d = get_rays(H, W, K, t(c2w))
+    o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+    rays = torch.cat([o, d, torch.full_like(d[:, :1], 2.), torch.full_like(d[:, :1], 6.), d / d.norm(dim=-1, keepdim=True)], -1)
+    lo, hi = t(np.float32(cases.BBOX_UNIT[0])), t(np.float32(cases.BBOX_UNIT[1]))
+    enc = lambda p: O.hash_encode(p, t(tables), lo, hi, O.level_resolutions(), 12)
+    ws = [t(w) for w in sig + col]
+    want = O.render_rays(rays.contiguous(), enc, (ws[:2], ws[2:]), None, 16, 0, white_bkgd=True, perturb=0.)
+    close(rgb.reshape(-1, 3), want["rgb_map"], 5e-5, atol=2e-5)
+    close(acc.reshape(-1), want["acc_map"], 5e-5, atol=2e-5)
+
+
 # ---------------------------------------------------------------------------------------------- next rows
 def test_radam_golden(golden):
     from radam import RAdam
@@ -494,7 +551,7 @@ def test_tv_loss_golden(golden):
     emb, tables = make_embedder(cases.BBOX_UNIT, 12)
     real = torch.randint
     for level in (0, 3, 7, 15):
-        torch.randint = lambda *a, **k: t(g[f"l{level}_min_vertex"]).clone()
+        torch.randint = lambda *a, **k: t(g[f"l{level}_min_vertex"]).clone()  # CPU tensor: loss.py moves it
         try:
             tv = total_variation_loss(emb.embeddings[level], emb.base_resolution, emb.finest_resolution, level, 12,
                                       n_levels=16)
