@@ -510,7 +510,7 @@ __device__ __forceinline__ void store_pair(const PairDesc& pr, const float4 (&re
 // 256 threads, one CTA per SM, two staging buffers: while the tensor core consumes pair q from buffer q & 1 the
 // threads split and store pair q + 1 into the other buffer and the global loads of pair q + 2 are in flight.
 __global__ void __launch_bounds__(kWThreads, 1)
-mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restrict__ dweights) {
+mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restrict__ dweights, int ablate) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
@@ -544,6 +544,8 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
     prefetch_pair(base_of(h), pairs[0], ra);
     prefetch_pair(base_of(h), pairs[1], rb);
   }
+  // profiling ablations (hn_set_tuning "mlp_dw_ablate"): 1 = no global loads after the first two, 2 = no MMAs,
+  // 4 = no split/store.  Results are wrong with any of them; they only apportion the kernel's time.
   int q = 0;
   for (; h < n_half; h += 2 * G) {
 #pragma unroll
@@ -563,7 +565,7 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
         mbar_wait(&bars[b], phase[b]);
         phase[b] ^= 1u;
       }
-      store_pair(pr, cur, Mhi, Mlo, Nhi, Nlo);
+      if (!(ablate & 4)) store_pair(pr, cur, Mhi, Mlo, Nhi, Nlo);
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
@@ -578,12 +580,14 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
         const uint64_t n_lo = kHiBits | (uint64_t)((smem_u32(Nlo) >> 4) & 0x3FFF);
         const uint32_t first = ((fresh >> i) & 1u) ? 0u : 1u;
         const uint32_t d = tmem + pr.col;
+        if (!(ablate & 2)) {
 #pragma unroll
-        for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_lo + 16 * s, n_hi + 16 * s, idesc, s ? 1u : first);
+          for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_lo + 16 * s, n_hi + 16 * s, idesc, s ? 1u : first);
 #pragma unroll
-        for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_hi + 16 * s, n_lo + 16 * s, idesc, 1u);
+          for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_hi + 16 * s, n_lo + 16 * s, idesc, 1u);
 #pragma unroll
-        for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_hi + 16 * s, n_hi + 16 * s, idesc, 1u);
+          for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_hi + 16 * s, n_hi + 16 * s, idesc, 1u);
+        }
         umma_commit(&bars[b]);
       }
       fresh &= ~(1u << i);
@@ -591,7 +595,7 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
       // refill this register set with step k + 2
       const int k2 = k + 2;
       const int64_t h2 = (k2 < 10) ? h + (k2 / 5) * G : h + 2 * G;
-      if (h2 < n_half) prefetch_pair(base_of(h2), pairs[k2 % 5], cur);
+      if (h2 < n_half && !(ablate & 1)) prefetch_pair(base_of(h2), pairs[k2 % 5], cur);
     }
   }
 #pragma unroll
@@ -672,6 +676,8 @@ int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   return check_launch("mlp_tc_fwd_kernel");
 }
 
+int g_mlp_dw_ablate = 0;
+
 int64_t mlp_tc_bwd_workspace_floats(int64_t N) {
   const int64_t tiles = (N + tc::kTile - 1) / tc::kTile;
   return tiles * tc::kWsRowsTc * tc::kTile;
@@ -707,7 +713,8 @@ int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t
     const int64_t halves = tiles * 2;
     const int64_t cap = (int64_t)sm_count();
     const unsigned grid = (unsigned)(halves < cap ? halves : cap);
-    tc::mlp_tc_bwd_weight_kernel<<<grid, tc::kWThreads, tc::kWeightSmemBytes, stream>>>(N, workspace, dweights);
+    tc::mlp_tc_bwd_weight_kernel<<<grid, tc::kWThreads, tc::kWeightSmemBytes, stream>>>(N, workspace, dweights,
+                                                                                        g_mlp_dw_ablate);
     return check_launch("mlp_tc_bwd_weight_kernel");
   }
 }
