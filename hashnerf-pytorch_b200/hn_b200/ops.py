@@ -175,8 +175,9 @@ def hash_encode_backward_sorted(xs4, dy, bbox6, resolutions, L, F, log2T, dtable
 
 
 # Points are re-ordered by grid cell before encoding when there are at least this many of them (the sort
-# costs a few passes over the points; below this size the launch overhead outweighs the coherence gain).
-SORT_MIN_POINTS = 1 << 20
+# costs a few passes over the points; measured crossover for uniformly random points: 2^18 plain 0.27 ms vs
+# sorted 0.31 ms, 2^19 0.52 vs 0.42 ms, 2^22 3.78 vs 2.20 ms -- tools/exp_threshold.py).
+SORT_MIN_POINTS = 1 << 19
 
 
 def sort_grid_res(n_points: int) -> int:
