@@ -1,0 +1,124 @@
+"""Out-of-bounds write detection without compute-sanitizer (closed on this pool): every output / workspace of the
+main entry points is carved out of a larger allocation whose surroundings hold a sentinel pattern; after the call
+the guard bands must be untouched.  Sizes are deliberately ragged (not multiples of any tile)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SENTINEL = 0x7FC0DEAD  # a quiet-NaN bit pattern no kernel produces
+GUARD = 4096           # bytes on each side
+
+
+class Guarded:
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        total = GUARD + ((self.nbytes + 15) // 16) * 16 + GUARD
+        self.buf = torch.full((total // 4,), SENTINEL, dtype=torch.int32, device=DEV)
+        self.ptr = self.buf.data_ptr() + GUARD
+        self.tail = GUARD + ((self.nbytes + 3) // 4) * 4  # first guard byte after the payload (4-byte granularity)
+
+    def view(self, dtype, shape):
+        n = int(np.prod(shape))
+        flat = self.buf.view(torch.uint8)[GUARD:GUARD + n * torch.empty((), dtype=dtype).element_size()]
+        return flat.view(dtype).view(shape)
+
+    def check(self, what):
+        b = self.buf
+        head = b[:GUARD // 4]
+        tail = b[(self.tail + 3) // 4:]
+        assert bool((head == SENTINEL).all()), f"{what}: wrote BEFORE the buffer"
+        assert bool((tail == SENTINEL).all()), f"{what}: wrote PAST the buffer"
+
+
+def _geom():
+    box = torch.tensor([-1.5] * 3 + [1.5] * 3, device=DEV)
+    res = torch.tensor([16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512.0], device=DEV)
+    return box, res
+
+
+@pytest.mark.parametrize("n", [1, 1000, 4099])
+def test_hash_encode_guard_bands(n):
+    from hn_b200 import _lib, ops
+    box, res = _geom()
+    L, F, T = 16, 2, 12
+    x = (torch.rand(n, 3, device=DEV) * 3.4 - 1.7).contiguous()       # some points outside the box
+    tables = torch.rand(L << T, F, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    out, keep, dt = Guarded(n * L * F * 4), Guarded(n), Guarded((L << T) * F * 4)
+    dt.view(torch.float32, ((L << T) * F,)).zero_()
+    dy = torch.randn(n, L * F, device=DEV)
+    _lib.call("hn_hash_encode_fwd", x.data_ptr(), tables.data_ptr(), box.data_ptr(), res.data_ptr(), n, L, F, T, out.ptr,
+              keep.ptr, s)
+    _lib.call("hn_hash_encode_bwd", x.data_ptr(), dy.data_ptr(), box.data_ptr(), res.data_ptr(), n, L, F, T, dt.ptr, s)
+    # sorted path: workspace, xs4 and the same outputs again
+    lib = _lib.load()
+    for grid in (16, 37):
+        ws, xs4 = Guarded(lib.hn_hash_sort_workspace_bytes(n, grid)), Guarded(n * 16)
+        _lib.call("hn_hash_sort_points", x.data_ptr(), box.data_ptr(), n, grid, ws.ptr, xs4.ptr, s)
+        _lib.call("hn_hash_encode_fwd_sorted", xs4.ptr, tables.data_ptr(), box.data_ptr(), res.data_ptr(), n, L, F, T,
+                  out.ptr, keep.ptr, s)
+        _lib.call("hn_hash_encode_bwd_sorted", xs4.ptr, dy.data_ptr(), box.data_ptr(), res.data_ptr(), n, L, F, T,
+                  dt.ptr, s)
+        torch.cuda.synchronize()
+        for g, w in ((ws, "sort workspace"), (xs4, "xs4")):
+            g.check(f"{w} (grid {grid})")
+    for g, w in ((out, "features"), (keep, "keep"), (dt, "dtables")):
+        g.check(w)
+    want, _ = ops.hash_encode_forward(x, tables, box, res, L, F, T)
+    assert torch.equal(out.view(torch.float32, (n, L * F)), want)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("n,ppv", [(1, 1), (1000, 1), (192 * 7 + 5, 192)])
+def test_mlp_guard_bands(n, ppv, impl):
+    from hn_b200 import _lib
+    _lib.set_tuning("mlp_impl", impl)
+    try:
+        lib = _lib.load()
+        s = torch.cuda.current_stream().cuda_stream
+        enc = (torch.randn(n, 32, device=DEV) * 0.3).contiguous()
+        views = torch.randn((n + ppv - 1) // ppv, 16, device=DEV)
+        w = torch.randn(9344, device=DEV) * 0.1
+        dout = torch.randn(n, 4, device=DEV)
+        out, d_enc, dw = Guarded(n * 16), Guarded(n * 32 * 4), Guarded(9344 * 4)
+        ws = Guarded(lib.hn_mlp_bwd_workspace_bytes(n))
+        dw.view(torch.float32, (9344,)).zero_()
+        _lib.call("hn_mlp_fwd", enc.data_ptr(), 32, views.data_ptr(), 16, ppv, w.data_ptr(), None, n, out.ptr, s)
+        _lib.call("hn_mlp_bwd", enc.data_ptr(), 32, views.data_ptr(), 16, ppv, w.data_ptr(), None, dout.data_ptr(), n,
+                  d_enc.ptr, dw.ptr, ws.ptr, s)
+        torch.cuda.synchronize()
+        for g, what in ((out, "mlp out"), (d_enc, "d_enc"), (dw, "dweights"), (ws, "mlp workspace")):
+            g.check(f"{what} (impl {impl})")
+        assert bool(torch.isfinite(out.view(torch.float32, (n, 4))).all())
+    finally:
+        _lib.set_tuning("mlp_impl", 1)
+
+
+@pytest.mark.parametrize("R,S,Ni", [(1, 3, 1), (37, 64, 128), (5, 33, 77)])
+def test_render_stage_guard_bands(R, S, Ni):
+    from hn_b200 import _lib
+    s = torch.cuda.current_stream().cuda_stream
+    raw = torch.randn(R, S, 4, device=DEV)
+    z = torch.sort(2 + 4 * torch.rand(R, S, device=DEV), -1).values.contiguous()
+    d = torch.randn(R, 3, device=DEV)
+    outs = {k: Guarded(n * 4) for k, n in (("rgb", R * 3), ("disp", R), ("acc", R), ("w", R * S), ("depth", R),
+                                           ("ent", R), ("draw", R * S * 4), ("smp", R * Ni), ("mrg", R * (S + Ni)),
+                                           ("std", R), ("z", R * S), ("pts", R * S * 3))}
+    _lib.call("hn_composite_fwd", raw.data_ptr(), z.data_ptr(), d.data_ptr(), None, R, S, 1, outs["rgb"].ptr,
+              outs["disp"].ptr, outs["acc"].ptr, outs["w"].ptr, outs["depth"].ptr, outs["ent"].ptr, s)
+    g = torch.randn(R, 3, device=DEV)
+    _lib.call("hn_composite_bwd", raw.data_ptr(), z.data_ptr(), d.data_ptr(), None, R, S, 1, g.data_ptr(), None, None,
+              None, None, None, outs["draw"].ptr, s)
+    u = torch.rand(R, Ni, device=DEV)
+    _lib.call("hn_resample", z.data_ptr(), outs["w"].ptr, u.data_ptr(), None, R, S, Ni, outs["smp"].ptr, outs["mrg"].ptr,
+              outs["std"].ptr, s)
+    rays = torch.randn(R, 11, device=DEV)
+    tv = torch.linspace(0, 1, S, device=DEV)
+    _lib.call("hn_coarse_z", rays[:, 6].data_ptr(), rays[:, 7].data_ptr(), 11, tv.data_ptr(), None, R, S, 0,
+              outs["z"].ptr, s)
+    _lib.call("hn_ray_points", rays.data_ptr(), rays[:, 3:].data_ptr(), 11, z.data_ptr(), R, S, outs["pts"].ptr, s)
+    torch.cuda.synchronize()
+    for k, gd in outs.items():
+        gd.check(k)
