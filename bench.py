@@ -213,6 +213,32 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False):
     return n_rand / ms * 1e3, ms
 
 
+def inference_frame_extra(dev, H=800, W=800):
+    """BASELINE configs[4] shape: one 800x800 frame = 640 000 rays x (64 + 128) samples, perturb 0, no_grad."""
+    from embedding.hash_encoding import HashEmbedder
+    from embedding.spherical_harmonic import SHEncoder
+    from models import NeRFSmall
+    from run_nerf_helpers import render, run_network
+    torch.manual_seed(0)
+    emb = HashEmbedder((torch.tensor(BBOX[0]), torch.tensor(BBOX[1])), log2_hashmap_size=19).to(dev)
+    mk = lambda: NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                           input_ch=32, input_ch_views=16).to(dev)
+    coarse, fine, sh = mk(), mk(), SHEncoder()
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = torch.tensor([[1, 0, 0, 0.0], [0, 1, 0, 0.0], [0, 0, 1, 4.0]], device=dev)
+
+    def frame():
+        with torch.no_grad():
+            render(H, W, K, chunk=1024 * 32, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True, network_fn=coarse,
+                   network_fine=fine, network_query_fn=qfn, N_samples=64, N_importance=128, embed_fn=emb, perturb=0.,
+                   raw_noise_std=0., white_bkgd=True)
+
+    ms = time_loop(frame, 3, 1) / 3
+    return ms
+
+
 def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
@@ -380,6 +406,9 @@ def run_ours(args):
             rps, ms = train_step_extra(dev, n_rand, steps=20, graphed=True)
             extra[f"train_rays_per_s_nrand{n_rand}_cuda_graph"] = round(rps, 1)
             extra[f"train_ms_per_step_nrand{n_rand}_cuda_graph"] = round(ms, 3)
+        ms = inference_frame_extra(dev)
+        extra["inference_800x800_ms_per_frame"] = round(ms, 2)
+        extra["inference_800x800_mrays_per_s"] = round(0.64 / ms * 1e3, 2)
         extra["train_step"] = ("render_rays 64+128 samples/ray, perturb=1, white_bkgd, mse+sparsity, backward, RAdam"
                                "; eager = the drop-in API driven like run_nerf.py:608-642 incl. the 16 TV-loss terms, cuda_graph "
                                "= hn_b200.graph.GraphedTrainStep replaying render+loss+backward+RAdam (no TV)")

@@ -123,3 +123,24 @@ def all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> t
     parts = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(parts, buf, group=group)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+@torch.no_grad()
+def render_image_sharded(H, W, K, c2w, render_fn, group=None):
+    """Inference partition of SURVEY 8e: every rank renders a contiguous range of the frame's H*W rays and the
+    per-ray results are all-gathered, so each rank returns the full (rgb [H,W,3], depth [H,W], acc [H,W]).
+
+    ``render_fn(rays_o [n,3], rays_d [n,3]) -> (rgb [n,3], depth [n], acc [n])`` is typically a closure over
+    ``run_nerf_helpers.render(H, W, K, rays=(o, d), ...)``."""
+    from ray_util import get_rays
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    rays_o, rays_d = get_rays(H, W, K, c2w)
+    rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+    start, stop = shard_range(H * W, rank, world)
+    rgb, depth, acc = render_fn(rays_o[start:stop], rays_d[start:stop])
+    local = torch.cat([rgb.reshape(-1, 3), depth.reshape(-1, 1), acc.reshape(-1, 1)], dim=-1)
+    if world > 1:
+        counts = [shard_range(H * W, r, world)[1] - shard_range(H * W, r, world)[0] for r in range(world)]
+        local = all_gather_rows(local.contiguous(), counts, group=group)
+    return local[:, :3].reshape(H, W, 3), local[:, 3].reshape(H, W), local[:, 4].reshape(H, W)

@@ -307,6 +307,22 @@ def gen_radam(ref):
          traj_p=np.stack(traj_p), traj_q=np.stack(traj_q))
 
 
+def gen_rays(ref):
+    rs = np.random.RandomState(71)
+    H, W, focal = 23, 31, 27.5
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    q, _ = np.linalg.qr(rs.randn(3, 3))
+    c2w = np.concatenate([q, rs.randn(3, 1)], -1).astype(np.float32)
+    o, d = ref.get_rays(H, W, K, T(c2w))
+    o_np, d_np = ref.get_rays_np(H, W, K, c2w)
+    # forward-facing pose for the NDC warp (looking down -z from z > 0)
+    c2w_f = np.array([[1, 0, 0, 0.05], [0, 1, 0, -0.02], [0, 0, 1, 0.3]], np.float32)
+    of, df = ref.get_rays(H, W, K, T(c2w_f))
+    no, nd = ref.get_ndc_rays(H, W, K[0][0], 1., of.reshape(-1, 3), df.reshape(-1, 3))
+    save("rays", H=H, W=W, focal=focal, c2w=c2w, rays_o=o.contiguous().numpy(), rays_d=d.numpy(),
+         rays_o_np=np.ascontiguousarray(o_np), rays_d_np=d_np, c2w_f=c2w_f, ndc_o=no.numpy(), ndc_d=nd.numpy())
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not found; golden vectors can only be regenerated where "
@@ -329,6 +345,7 @@ def main():
     gen_render_rays(ref, "render_rays_det_noise", cases.BBOX_ODD, 0.0, False, 1.0)
     gen_tv(ref)
     gen_radam(ref)
+    gen_rays(ref)
 
 
 if __name__ == "__main__":

@@ -375,6 +375,35 @@ def render_rays(ray_batch: torch.Tensor, enc, coarse_w, fine_w, n_samples: int, 
 
 
 # ----------------------------------------------------------------------------------------------
+# section 8f "next" row 3: ray generation
+# ----------------------------------------------------------------------------------------------
+def pinhole_rays(H: int, W: int, K, c2w: torch.Tensor):
+    """ray_util.py:62-80 -- (rays_o, rays_d), each [H, W, 3]."""
+    cols = torch.linspace(0, W - 1, W)
+    rows = torch.linspace(0, H - 1, H)
+    j, i = torch.meshgrid(rows, cols, indexing="ij")                                  # :71-73 (ij meshgrid, then .t())
+    cam = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1)   # :74
+    rays_d = torch.sum(cam[..., None, :] * c2w[:3, :3], -1)                           # :77
+    rays_o = c2w[:3, -1].expand(rays_d.shape)                                         # :79
+    return rays_o, rays_d
+
+
+def ndc_rays(H: int, W: int, focal: float, near: float, rays_o: torch.Tensor, rays_d: torch.Tensor):
+    """ray_util.py:96-142 -- forward-facing scenes: shift origins to the near plane, project to NDC."""
+    t = -(near + rays_o[..., 2]) / rays_d[..., 2]                                     # :119
+    rays_o = rays_o + t[..., None] * rays_d                                           # :120
+    ox_oz = rays_o[..., 0] / rays_o[..., 2]                                           # :124
+    oy_oz = rays_o[..., 1] / rays_o[..., 2]
+    o0 = -1. / (W / (2. * focal)) * ox_oz                                             # :129
+    o1 = -1. / (H / (2. * focal)) * oy_oz
+    o2 = 1. + 2. * near / rays_o[..., 2]
+    d0 = -1. / (W / (2. * focal)) * (rays_d[..., 0] / rays_d[..., 2] - ox_oz)         # :134
+    d1 = -1. / (H / (2. * focal)) * (rays_d[..., 1] / rays_d[..., 2] - oy_oz)
+    d2 = 1 - o2
+    return torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)               # :139-140
+
+
+# ----------------------------------------------------------------------------------------------
 # section 8f "next" rows: TV loss and RAdam (restated for the kernels that replace them)
 # ----------------------------------------------------------------------------------------------
 def total_variation(table: torch.Tensor, min_res: int, max_res: int, level: int,

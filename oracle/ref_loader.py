@@ -77,6 +77,11 @@ def load(device: str = "cpu") -> types.SimpleNamespace:
                     NeRFSmall=models_mod.NeRFSmall, NeRF=models_mod.NeRF,
                     RAdam=radam_mod.RAdam))
 
+    # ray_util.py imports kornia (not installed) for the st3d helpers only; blank that line (:3)
+    ray_src = _read("ray_util.py")
+    ray_src = [("" if (i + 1) == 3 else ln) for i, ln in enumerate(ray_src)]
+    ray_mod = _exec_module("_ref_ray_util", "ray_util.py", ray_src)
+
     loss_src = _read("loss.py")
     loss_src = [("" if (i + 1) == 8 else ln) for i, ln in enumerate(loss_src)]
     loss_mod = _exec_module("_ref_loss", "loss.py", loss_src, inject=dict(hash=hash_mod.hash))
@@ -91,6 +96,8 @@ def load(device: str = "cpu") -> types.SimpleNamespace:
         run_network=helpers_mod.run_network, render_rays=helpers_mod.render_rays,
         raw2outputs=helpers_mod.raw2outputs, sample_pdf=helpers_mod.sample_pdf,
         total_variation_loss=loss_mod.total_variation_loss, RAdam=radam_mod.RAdam,
+        ray_util=ray_mod, get_rays=ray_mod.get_rays, get_rays_np=ray_mod.get_rays_np,
+        get_ndc_rays=ray_mod.get_ndc_rays,
     )
     _CACHE[device] = ns
     return ns

@@ -497,6 +497,52 @@ def test_get_rays_and_pack_rays():
     assert ops.pack_rays(rays_o, rays_d, None, 0.0, 1.0).shape == (H * W, 8)
 
 
+def test_get_rays_golden(golden):
+    from ray_util import get_rays, get_ndc_rays
+    g = golden("rays")
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    o, d = get_rays(H, W, K, g32(g["c2w"]))                       # hn_get_rays
+    bit_equal(d, g["rays_d"])                                      # same roundings as the reference's chain
+    bit_equal(o.contiguous(), g["rays_o"])
+    of, df = get_rays(H, W, K, g32(g["c2w_f"]))
+    no, nd = get_ndc_rays(H, W, K[0][0], 1., of.reshape(-1, 3), df.reshape(-1, 3))
+    close(no, g["ndc_o"], 2e-6, atol=1e-6)
+    close(nd, g["ndc_d"], 2e-6, atol=1e-6)
+
+
+def test_render_ndc_forward_facing_against_oracle():
+    """LLFF-style path (BASELINE configs[4], fern.txt shapes scaled down): NDC warp, N_importance = N_samples,
+    no white background; coarse outputs strict, fine outputs modulo the resampling branch chaos."""
+    from embedding.spherical_harmonic import SHEncoder
+    from run_nerf_helpers import render, run_network
+    H, W, focal = 9, 12, 11.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = np.array([[1, 0, 0, 0.05], [0, 1, 0, -0.02], [0, 0, 1, 0.3]], np.float32)
+    bbox = ((-1.6, -1.6, -1.1), (1.6, 1.6, 1.1))
+    emb, tables = make_embedder(bbox, 12, scale=3000.0)
+    w_c, w_f = sum(cases.mlp_weights(5), []), sum(cases.mlp_weights(6), [])
+    coarse, fine, sh = make_mlp(w_c), make_mlp(w_f), SHEncoder()
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    with torch.no_grad():
+        rgb, depth, acc, extras = render(H, W, K, chunk=64, c2w=g32(c2w), ndc=True, near=0., far=1.,
+                                         use_viewdirs=True, network_fn=coarse, network_fine=fine,
+                                         network_query_fn=qfn, N_samples=16, N_importance=16, embed_fn=emb,
+                                         perturb=0., raw_noise_std=0., white_bkgd=False)
+    o, d = O.pinhole_rays(H, W, K, t(c2w))
+    o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+    vd = d / torch.norm(d, dim=-1, keepdim=True)
+    no, nd = O.ndc_rays(H, W, K[0][0], 1., o, d)
+    rays = torch.cat([no, nd, torch.zeros_like(nd[:, :1]), torch.ones_like(nd[:, :1]), vd], -1).contiguous()
+    lo, hi = t(np.float32(bbox[0])), t(np.float32(bbox[1]))
+    enc = lambda p: O.hash_encode(p, t(tables), lo, hi, O.level_resolutions(), 12)
+    cw, fw = [t(w) for w in w_c], [t(w) for w in w_f]
+    want = O.render_rays(rays, enc, (cw[:2], cw[2:]), (fw[:2], fw[2:]), 16, 16, white_bkgd=False, perturb=0.)
+    close(extras["rgb0"].reshape(-1, 3), want["rgb0"], 5e-5, atol=2e-5)
+    close(extras["acc0"].reshape(-1), want["acc0"], 5e-5, atol=2e-5)
+    mostly_close(rgb.reshape(-1, 3), want["rgb_map"], 5e-5, 2e-5, 0.9, what="fine rgb")
+
+
 def test_render_full_image_against_oracle():
     """render(c2w=...) -> get_rays -> pack -> chunked render_rays, coarse only, vs the oracle on the same rays."""
     from embedding.spherical_harmonic import SHEncoder

@@ -203,3 +203,25 @@ def test_radam(golden):
         lr = 0.01 * (0.1 ** ((step + 1) / 10000.0))
         np.testing.assert_allclose(p.numpy(), g["traj_p"][step], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(q.numpy(), g["traj_q"][step], rtol=1e-6, atol=1e-12)
+
+
+def test_rays(golden):
+    g = golden("rays")
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    o, d = O.pinhole_rays(H, W, K, t(g["c2w"]))
+    assert_bit_exact(d, g["rays_d"])
+    assert_bit_exact(o.contiguous(), g["rays_o"])
+    of, df = O.pinhole_rays(H, W, K, t(g["c2w_f"]))
+    no, nd = O.ndc_rays(H, W, K[0][0], 1., of.reshape(-1, 3), df.reshape(-1, 3))
+    assert_bit_exact(no, g["ndc_o"])
+    assert_bit_exact(nd, g["ndc_d"])
+    # the package's CPU-side ray helpers (numpy variant and the torch branch used for CPU poses)
+    from ray_util import get_rays, get_rays_np, get_ndc_rays
+    o2, d2 = get_rays(H, W, K, t(g["c2w"]))
+    assert_bit_exact(d2, g["rays_d"])
+    on, dn = get_rays_np(H, W, K, g["c2w"])
+    np.testing.assert_array_equal(dn, g["rays_d_np"])
+    no2, nd2 = get_ndc_rays(H, W, K[0][0], 1., of.reshape(-1, 3), df.reshape(-1, 3))
+    assert_bit_exact(no2, g["ndc_o"])
+    assert_bit_exact(nd2, g["ndc_d"])
