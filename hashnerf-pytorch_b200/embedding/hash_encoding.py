@@ -142,15 +142,18 @@ class HashEmbedder(nn.Module):
             self._sink = ops.GradSink(self._level_weights())
         return self._sink
 
-    def encode(self, x):
-        """Same as forward() but the mask stays the kernel's uint8 (what the fused MLP consumes)."""
+    def encode(self, x, ordered=False):
+        """Same as forward() but the mask stays the kernel's uint8 (what the fused MLP consumes).  ``ordered``:
+        the caller vouches that consecutive points are spatial neighbours (samples along rays, as run_network
+        produces them): sorting such points only costs (measured 800x800 frame: 159 ms sorted vs 69 ms as given)."""
         lead = x.shape[:-1]
         pts = x.reshape(-1, 3)
         box, res = self._geometry(pts.device)
         self._flatten_parameters()
         sink = self.grad_sink() if torch.is_grad_enabled() else None
         feats, keep = ops.HashEncodeFn.apply(pts, box, res, self.log2_hashmap_size, self.n_features_per_level,
-                                             self.coherent, sink, *self._level_weights())
+                                             "ordered" if (ordered and self.coherent is None) else self.coherent, sink,
+                                             *self._level_weights())
         if len(lead) != 1:
             feats, keep = feats.reshape(*lead, self.out_dim), keep.reshape(lead)
         return feats, keep

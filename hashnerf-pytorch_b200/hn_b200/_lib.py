@@ -26,6 +26,7 @@ SIGNATURES = {
     "hn_voxel_vertices": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p]),
     "hn_hash_encode_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _p]),
     "hn_hash_encode_bwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
+    "hn_hash_encode_bwd_ordered": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
     "hn_hash_sort_workspace_bytes": (_l, [_l, _i]),
     "hn_hash_sort_points": (_i, [_p, _p, _l, _i, _p, _p, _p]),
     "hn_hash_encode_fwd_sorted": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _p]),

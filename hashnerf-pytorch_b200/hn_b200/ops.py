@@ -129,12 +129,13 @@ def hash_encode_forward(x, tables_flat, bbox6, resolutions, L, F, log2T, want_ke
     return out, keep
 
 
-def hash_encode_backward(x, dy, bbox6, resolutions, L, F, log2T, dtables_flat):
-    """Accumulates into ``dtables_flat`` ([L * 2^T * F] fp32)."""
+def hash_encode_backward(x, dy, bbox6, resolutions, L, F, log2T, dtables_flat, ordered=False):
+    """Accumulates into ``dtables_flat`` ([L * 2^T * F] fp32).  ``ordered``: the points are spatially coherent
+    in their given order (ray samples) -> warp-aggregated scatter."""
     dev = _need_cuda(x, dy, bbox6, resolutions, dtables_flat)
     x, dy = _f32c(x), _f32c(dy)
     with _on(dev):
-        _lib.call("hn_hash_encode_bwd", x.data_ptr(), dy.data_ptr(), bbox6.data_ptr(), resolutions.data_ptr(),
+        _lib.call("hn_hash_encode_bwd_ordered" if ordered else "hn_hash_encode_bwd", x.data_ptr(), dy.data_ptr(), bbox6.data_ptr(), resolutions.data_ptr(),
                   x.shape[0], L, F, log2T, dtables_flat.data_ptr(), _stream())
 
 
@@ -246,7 +247,8 @@ class HashEncodeFn(torch.autograd.Function):
     table gradient to each of them; the gradients returned are slices of ONE flat buffer filled by a
     single scatter kernel (the reference produces 16 separate dense gradients through
     embedding_dense_backward, hash_encoding.py:106).  ``coherent``: None = sort the points by grid cell when
-    there are many of them, True / False = force.  ``sink``: a GradSink (gradients accumulate in place into its
+    there are many of them, True / False = force, "ordered" = the points are already spatially coherent in the
+    given order (consecutive samples of rays): never sort, aggregate the scatter.  ``sink``: a GradSink (gradients accumulate in place into its
     persistent buffer and ``param.grad`` points at it) or None (plain autograd return values)."""
 
     @staticmethod
@@ -255,7 +257,11 @@ class HashEncodeFn(torch.autograd.Function):
         ctx.sink = sink
         flat = pack(level_tables)
         N = x.shape[0]
-        use_sort = (N >= SORT_MIN_POINTS) if coherent is None else (bool(coherent) and N > 0)
+        ordered = isinstance(coherent, str) and coherent == "ordered"
+        if ordered:
+            use_sort = False
+        else:
+            use_sort = (N >= SORT_MIN_POINTS) if coherent is None else (bool(coherent) and N > 0)
         if use_sort:
             xs4 = hash_sort_points(x, bbox6, sort_grid_res(N))
             out, keep = hash_encode_forward_sorted(xs4, flat, bbox6, resolutions, L, F, log2T)
@@ -263,21 +269,21 @@ class HashEncodeFn(torch.autograd.Function):
         else:
             out, keep = hash_encode_forward(x, flat, bbox6, resolutions, L, F, log2T)
             ctx.save_for_backward(x, bbox6, resolutions)
-        ctx.meta = (L, F, log2T, use_sort)
+        ctx.meta = (L, F, log2T, use_sort, ordered)
         ctx.mark_non_differentiable(keep)
         return out, keep  # keep: uint8 (HashEmbedder.forward converts to bool for the caller)
 
     @staticmethod
     def backward(ctx, dout, _dkeep):
         x, bbox6, resolutions = ctx.saved_tensors
-        L, F, log2T, use_sort = ctx.meta
+        L, F, log2T, use_sort, ordered = ctx.meta
         T = 1 << log2T
         sink = ctx.sink
         dflat = sink.acquire() if sink is not None else torch.zeros(L * T * F, dtype=torch.float32, device=x.device)
         if use_sort:
             hash_encode_backward_sorted(x, dout, bbox6, resolutions, L, F, log2T, dflat)
         else:
-            hash_encode_backward(x, dout, bbox6, resolutions, L, F, log2T, dflat)
+            hash_encode_backward(x, dout, bbox6, resolutions, L, F, log2T, dflat, ordered=ordered)
         if sink is not None:  # accumulated in place; param.grad already points into the buffer
             return (None,) * (7 + L)
         grads = dflat.view(L, T, F).unbind(0)

@@ -68,6 +68,11 @@ HN_API int hn_hash_encode_fwd(const float* x, const float* tables, const float* 
 HN_API int hn_hash_encode_bwd(const float* x, const float* dy, const float* bbox, const float* resolutions,
                        int64_t N, int L, int F, int log2T, float* dtables, void* stream);
 
+/* Same as hn_hash_encode_bwd for points the caller knows to be spatially coherent in their given order
+ * (consecutive samples of a ray): lanes of a warp that fall in the same voxel are summed before the atomics. */
+HN_API int hn_hash_encode_bwd_ordered(const float* x, const float* dy, const float* bbox, const float* resolutions,
+                                      int64_t N, int L, int F, int log2T, float* dtables, void* stream);
+
 /* Coherent ("sorted") variant of the two calls above.  hn_hash_sort_points bins the points into a
  * grid_res^3 grid over the bbox (counting sort, x fastest) and writes xs4[i] = (x, y, z, bit-cast original
  * row) for the i-th point in cell order; the *_sorted calls process that order -- gathers coalesce / hit L1,
