@@ -89,8 +89,14 @@ class HashEmbedder(nn.Module):
     def _flatten_parameters(self):
         """Re-home the level tables into one contiguous buffer (keeps Parameter identity)."""
         ws = self._level_weights()
-        if ops._consecutive(ws):
+        # cheap steady-state check: the end points of the span are where a flat buffer puts them
+        if getattr(self, "_flat_ok", False) and \
+                ws[-1].data_ptr() - ws[0].data_ptr() == (len(ws) - 1) * ws[0].numel() * 4:
             return
+        if ops._consecutive(ws):
+            self._flat_ok = True
+            return
+        self._flat_ok = True
         flat = torch.empty(len(ws), *ws[0].shape, dtype=torch.float32, device=ws[0].device)
         with torch.no_grad():
             for l, w in enumerate(ws):
@@ -99,6 +105,7 @@ class HashEmbedder(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)  # .to()/.cuda() move each level separately
+        self._flat_ok = False
         self._flatten_parameters()
         self._geom_cache = {}
         return out

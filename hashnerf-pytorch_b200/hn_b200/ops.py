@@ -47,7 +47,14 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw getter avoids building a Stream
+    object per call; it is what the launch-overhead-bound eager path spends its time on otherwise)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -79,10 +86,11 @@ def _consecutive(tensors: Sequence[torch.Tensor]) -> bool:
     return True
 
 
-def pack(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+def pack(tensors: Sequence[torch.Tensor], known_flat: bool = False) -> torch.Tensor:
     """One flat fp32 view over ``tensors`` -- zero-copy when they already are slices of one flat buffer
-    (the layout HashEmbedder / NeRFSmall allocate), otherwise a packed copy."""
-    if _consecutive(tensors):
+    (the layout HashEmbedder / NeRFSmall allocate), otherwise a packed copy.  ``known_flat``: the caller has
+    just verified the layout."""
+    if known_flat or _consecutive(tensors):
         n = sum(t.numel() for t in tensors)
         return torch.as_strided(tensors[0].detach(), (n,), (1,))
     return torch.cat([t.detach().reshape(-1).float() for t in tensors])

@@ -60,7 +60,32 @@ class RAdam(Optimizer):
 
     def _spans(self):
         """[(group, [params])]: maximal runs of parameters whose data, gradients and moments are each back to
-        back in one storage and whose step counts agree -- each run is updated by one kernel launch."""
+        back in one storage and whose step counts agree -- each run is updated by one kernel launch.  The plan is
+        cached and re-validated per step by gradient pointers (gradients normally live in persistent buffers; all
+        parameters of a cached span advance their step counts together, so the counts stay equal)."""
+        cached = getattr(self, "_span_cache", None)
+        if cached is not None:
+            sig, spans = cached
+            ok = True
+            for group in self.param_groups:
+                for p in group['params']:
+                    g = p.grad
+                    if (None if g is None else g.data_ptr()) != sig.get(id(p)):
+                        ok = False
+                        break
+                if not ok:
+                    break
+            if ok:
+                return spans
+        spans = self._compute_spans()
+        sig = {}
+        for group in self.param_groups:
+            for p in group['params']:
+                sig[id(p)] = None if p.grad is None else p.grad.data_ptr()
+        self._span_cache = (sig, spans)
+        return spans
+
+    def _compute_spans(self):
         out = []
         for group in self.param_groups:
             active = [p for p in group['params'] if p.grad is not None]
