@@ -453,7 +453,7 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 // ================================================================================================
 constexpr int kHalf = 64;
 constexpr uint32_t cW0 = 0, cW1 = 32, cW2 = 48, cW3 = 80, cW4 = 144;  // accumulator columns
-constexpr size_t kWeightSmemBytes = (size_t)2 * 4 * 64 * kHalf * sizeof(float);  // 2 x (M_hi | M_lo | N_hi | N_lo) = 128 KB
+constexpr size_t kWeightBufBytes = (size_t)4 * 64 * kHalf * sizeof(float);  // (M_hi | M_lo | N_hi | N_lo) = 64 KB
 
 // Staging of one operand pair for a 64-point half tile.  Slot s of thread t covers float4 number s*128 + t of
 // the pair: the first 1024 belong to the 64 M-side rows, the rest to the N-side rows.  Within an operand,
@@ -507,9 +507,12 @@ __device__ __forceinline__ void store_pair(const PairDesc& pr, const float4 (&re
   }
 }
 
-// 256 threads, one CTA per SM, two staging buffers: while the tensor core consumes pair q from buffer q & 1 the
-// threads split and store pair q + 1 into the other buffer and the global loads of pair q + 2 are in flight.
-__global__ void __launch_bounds__(kWThreads, 1)
+// 256 threads.  NBUF = 2: one CTA per SM, two staging buffers -- while the tensor core consumes pair q from
+// buffer q & 1 the threads split and store pair q + 1 into the other buffer and the global loads of pair q + 2
+// are in flight.  NBUF = 1: one staging buffer and two CTAs per SM -- the second CTA fills the bubbles of the
+// first (its MMA wait, its barrier, its load latency) instead of a second buffer.
+template <int NBUF>
+__global__ void __launch_bounds__(kWThreads, NBUF == 1 ? 2 : 1)
 mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restrict__ dweights, int ablate) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[2];
@@ -555,7 +558,7 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
       const int i = k % 5;
       float4(&cur)[kSlots] = (k & 1) ? rb : ra;
       const PairDesc pr = pairs[i];
-      const int b = q & 1;
+      const int b = (NBUF == 2) ? (q & 1) : 0;
       ++q;
       float* Mhi = smem + b * (4 * 64 * kHalf);
       float* Mlo = Mhi + 64 * kHalf;
@@ -677,6 +680,7 @@ int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t
 }
 
 int g_mlp_dw_ablate = 0;
+int g_mlp_dw_nbuf = 1;  // 1: single staging buffer, two CTAs per SM; 2: double buffer, one CTA per SM
 
 int64_t mlp_tc_bwd_workspace_floats(int64_t N) {
   const int64_t tiles = (N + tc::kTile - 1) / tc::kTile;
@@ -694,9 +698,12 @@ int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t
     e = cudaFuncSetAttribute(tc::mlp_tc_bwd_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)tc::kDeltaSmemBytes);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_delta_kernel)");
-    e = cudaFuncSetAttribute(tc::mlp_tc_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)tc::kWeightSmemBytes);
-    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_weight_kernel)");
+    e = cudaFuncSetAttribute(tc::mlp_tc_bwd_weight_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)tc::kWeightBufBytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_weight_kernel<1>)");
+    e = cudaFuncSetAttribute(tc::mlp_tc_bwd_weight_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(2 * tc::kWeightBufBytes));
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_weight_kernel<2>)");
     done_dev = dev;
   }
   const int64_t tiles = (N + tc::kTile - 1) / tc::kTile;
@@ -711,10 +718,15 @@ int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   }
   {
     const int64_t halves = tiles * 2;
-    const int64_t cap = (int64_t)sm_count();
+    const int nbuf = g_mlp_dw_nbuf == 2 ? 2 : 1;
+    const int64_t cap = (int64_t)sm_count() * (nbuf == 1 ? 2 : 1);
     const unsigned grid = (unsigned)(halves < cap ? halves : cap);
-    tc::mlp_tc_bwd_weight_kernel<<<grid, tc::kWThreads, tc::kWeightSmemBytes, stream>>>(N, workspace, dweights,
-                                                                                        g_mlp_dw_ablate);
+    if (nbuf == 1)
+      tc::mlp_tc_bwd_weight_kernel<1><<<grid, tc::kWThreads, tc::kWeightBufBytes, stream>>>(N, workspace, dweights,
+                                                                                           g_mlp_dw_ablate);
+    else
+      tc::mlp_tc_bwd_weight_kernel<2><<<grid, tc::kWThreads, 2 * tc::kWeightBufBytes, stream>>>(
+          N, workspace, dweights, g_mlp_dw_ablate);
     return check_launch("mlp_tc_bwd_weight_kernel");
   }
 }

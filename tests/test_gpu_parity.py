@@ -188,6 +188,44 @@ def test_hash_encode_coherent_path_vs_oracle(log2T, bbox, n, agg):
     bit_equal(xs4[:, :3], g32(x)[rows])
 
 
+@pytest.mark.parametrize("bbox", [cases.BBOX_ODD, cases.BBOX_UNIT,
+                                  ((-3e-21, -1e-21, -2e-21), (1e-21, 4e-21, 2e-21)),      # cell sizes below 2^-60
+                                  ((-7.3e5, -1.1e6, -2.0e5), (9.1e5, 4.4e5, 8.8e5)),
+                                  ((0.0, 0.0, 0.0), (1.0, 3.0, 7.0))])
+@pytest.mark.parametrize("coherent", [False, True])
+def test_hash_encode_cell_boundaries_bit_exact(bbox, coherent):
+    """Points sitting exactly on (and one ulp either side of) voxel faces of every level: the quotient
+    (x - min) / g is within an ulp of an integer there, so any division that is not correctly rounded moves a
+    point into the neighbouring voxel.  Pins the hoisted-reciprocal division against the reference's true
+    division, on both sides of its range switch (LevelGeom::fast)."""
+    log2T = 14
+    emb, tables = make_embedder(bbox, log2T)
+    emb.coherent = coherent
+    lo32, hi32 = np.float32(bbox[0]), np.float32(bbox[1])
+    res = O.level_resolutions().numpy().astype(np.float32)
+    rs = np.random.RandomState(99)
+    pts = []
+    for l in range(16):
+        g = (hi32 - lo32) / res[l]                                   # fp32, as the reference computes it
+        k = rs.randint(0, int(res[l]) + 1, size=(600, 3)).astype(np.float32)
+        base = (k * g + lo32).astype(np.float32)
+        pts += [base, np.nextafter(base, np.float32(np.inf)), np.nextafter(base, np.float32(-np.inf))]
+    tiny = np.float32(bbox[0]) + np.float32([1e-45, 1e-40, 1e-38]) * rs.rand(64, 3).astype(np.float32)
+    x = np.concatenate(pts + [tiny.astype(np.float32)]).astype(np.float32)
+    lo, hi = t(lo32), t(hi32)
+    want, want_keep = O.hash_encode(t(x), t(tables), lo, hi, O.level_resolutions(), log2T)
+    out, keep = emb(g32(x))
+    bit_equal(out, want)
+    bit_equal(keep, want_keep)
+    # the stand-alone voxel kernel (true division per point) and the encoder's hoisted division agree on cells
+    hashed, vmin, vmax = emb.voxel_vertices(g32(x))
+    xyz = t(x)
+    for l in range(16):
+        xyz, _, wmin, wmax, whash, _ = O.voxel_vertices(xyz, lo, hi, O.level_resolutions()[l], log2T)
+        bit_equal(vmin[l], wmin)
+        bit_equal(hashed[l], whash)
+
+
 @pytest.mark.parametrize("n", [0, 1, 255, 257])
 def test_hash_encode_ragged_and_empty(n):
     emb, tables = make_embedder(cases.BBOX_ODD, 10)
