@@ -327,45 +327,86 @@ def run_ours(args):
                                           / (sort_ms + fwd_ms + bwd_ms) / 1e6 / peak, 4)}
 
     # ---- end to end through the public API with host inputs
+    # The user-level pattern for host-resident points (a data loader with one step of prefetch): every step
+    # uploads ITS input points from pinned host memory into one of two device buffers on a copy stream; the
+    # upload of step s+1 is issued when step s starts computing, so it overlaps step s's kernels.  Every timed
+    # step therefore contains one full H2D upload (201 MB), the encode + scatter through HashEmbedder.forward /
+    # autograd, and the D2H read of the step's result; the piecewise variant (--e2e-chunks > 1) instead splits
+    # one step's points into geometric pieces and overlaps piece c+1's upload with piece c's compute.
     x_host = x.cpu().pin_memory()
-    x_dev = torch.empty_like(x)
     result_host = torch.empty(L, dtype=torch.float32).pin_memory()
-
-    n_chunks = 4
-    bounds = [(i * n // n_chunks, (i + 1) * n // n_chunks) for i in range(n_chunks)]
     copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event() for _ in range(n_chunks)]
-    consumed = [torch.cuda.Event() for _ in range(n_chunks)]
+    n_chunks = max(1, args.e2e_chunks)
 
-    def e2e_step():
-        # The user-level pattern for host-resident points: upload chunk c+1 on a copy stream while chunk c is
-        # encoded (HashEmbedder.forward) and back-propagated; gradients accumulate across chunks.
-        main = torch.cuda.current_stream()
-        for e in emb.embeddings:
-            e.weight.grad = None
-        for c, (a, b) in enumerate(bounds):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[c])              # previous step's kernels are done with the buffer
-                x_dev[a:b].copy_(x_host[a:b], non_blocking=True)  # H2D of this step's input points
-                copied[c].record(copy_stream)
-        for c, (a, b) in enumerate(bounds):
-            main.wait_event(copied[c])
-            feats, _keep = emb(x_dev[a:b])                       # HashEmbedder.forward (public API)
-            feats.backward(dy[a:b])                              # autograd -> scatter kernel
-            consumed[c].record(main)
+    def finish_step(main):
         g = emb.grad_sink().flat.view(L, -1).sum(dim=1)
         if dist is not None:
             dist.all_reduce(g)
         result_host.copy_(g, non_blocking=True)                  # D2H of the step's result (per-level grad sums)
         main.synchronize()
 
+    if n_chunks == 1:
+        x_bufs = [torch.empty_like(x), torch.empty_like(x)]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {"cur": 0}
+
+        def upload(b):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])              # the kernels that read this buffer are done
+                x_bufs[b].copy_(x_host, non_blocking=True)       # H2D of one step's input points
+                copied[b].record(copy_stream)
+
+        upload(0)                                                # prologue: the first step's input
+
+        def e2e_step():
+            main = torch.cuda.current_stream()
+            b = state["cur"]
+            for e in emb.embeddings:
+                e.weight.grad = None
+            main.wait_event(copied[b])
+            upload(b ^ 1)                                        # next step's input, overlapping this step
+            feats, _keep = emb(x_bufs[b])                        # HashEmbedder.forward (public API)
+            feats.backward(dy)                                   # autograd -> scatter kernel
+            consumed[b].record(main)
+            state["cur"] = b ^ 1
+            finish_step(main)
+
+        api = ("HashEmbedder.forward + autograd backward; each step's points are uploaded from pinned host memory "
+               "into one of two device buffers on a copy stream, issued one step ahead (prefetch depth 1) so the "
+               "upload overlaps the previous step's kernels; upstream gradient dY resident (stands for the "
+               "downstream MLP); per-level gradient sums read back every step")
+    else:
+        x_dev = torch.empty_like(x)
+        edges = [0] + [n * ((1 << (i + 1)) - 1) // ((1 << n_chunks) - 1) for i in range(n_chunks)]
+        bounds = [(edges[i], edges[i + 1]) for i in range(n_chunks)]
+        copied = [torch.cuda.Event() for _ in range(n_chunks)]
+        consumed = [torch.cuda.Event() for _ in range(n_chunks)]
+
+        def e2e_step():
+            main = torch.cuda.current_stream()
+            for e in emb.embeddings:
+                e.weight.grad = None
+            for c, (a, b) in enumerate(bounds):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[c])
+                    x_dev[a:b].copy_(x_host[a:b], non_blocking=True)
+                    copied[c].record(copy_stream)
+            for c, (a, b) in enumerate(bounds):
+                main.wait_event(copied[c])
+                feats, _keep = emb(x_dev[a:b])
+                feats.backward(dy[a:b])
+                consumed[c].record(main)
+            finish_step(main)
+
+        api = ("HashEmbedder.forward + autograd backward per piece (sizes 1:2:4:...), piece c+1 uploaded from pinned "
+               "host memory on a copy stream while piece c computes; dY resident; per-level gradient sums read back")
+
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = time_loop(e2e_step, e2e_steps, 2, dist) / e2e_steps
+    torch.cuda.synchronize()
     e2e = {"value": round(world * n / e2e_ms / 1e3, 2), "unit": "Msamples/s", "h2d_bytes_per_step": n * 12,
-           "d2h_bytes_per_step": L * 4, "ms_per_step": round(e2e_ms, 3),
-           "api": "HashEmbedder.forward + autograd backward on 4 chunks, chunk c+1 uploaded from pinned host memory "
-                  "on a copy stream while chunk c computes; upstream gradient dY resident (stands for the "
-                  "downstream MLP); per-level gradient sums read back"}
+           "d2h_bytes_per_step": L * 4, "ms_per_step": round(e2e_ms, 3), "chunks": n_chunks, "api": api}
 
     if rank != 0:
         if dist is not None:
@@ -376,7 +417,7 @@ def run_ours(args):
     # ---- extras (rank 0 only, N=1 only): other table sizes, training step
     extra = {}
     if world == 1 and not args.no_extra:
-        del x_host, x_dev
+        x_host = x_dev = x_bufs = None  # release the e2e buffers before the extra workloads
         for t_log2 in (14, 22):
             e2 = HashEmbedder((lo.cpu(), hi.cpu()), log2_hashmap_size=t_log2).to(dev)
             tb, (bx, rs) = e2.flat_tables(), e2._geometry(dev)
@@ -440,6 +481,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2T", type=int, default=19)
     ap.add_argument("--points", type=int, default=1 << 24)
+    ap.add_argument("--e2e-chunks", type=int, default=1,
+                    help="1 = upload each step's points one step ahead (double buffer); >1 = split one step into "
+                         "geometric pieces and overlap piece c+1's upload with piece c's compute")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
