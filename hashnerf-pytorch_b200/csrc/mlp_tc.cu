@@ -223,6 +223,7 @@ constexpr size_t kFwdSmemBytes = (size_t)2 * kImg * sizeof(float);  // 77,824
 // Everything the weight gradients need is written feature-major to the workspace:
 //   per 128-point tile a [472][128] fp32 block; row r, point p at  r * 128 + p  (coalesced across the warp)
 // ================================================================================================
+constexpr int kWsStride = 64;  // samples per workspace row: a tile is stored as two 64-point half blocks
 constexpr int rH1 = 0, rC = 64, rH3 = 96, rH4 = 160, rDz1 = 224, rDh2 = 288, rDz3 = 304, rDz4 = 368, rIn = 432,
               rDrgb = 464, kWsRowsTc = 472;
 // transposed weight images for the dX chain (canonical K-major [N][K]), appended after the forward images
@@ -264,7 +265,7 @@ __device__ __forceinline__ uint64_t epilogue64(uint32_t row, float* __restrict__
         v[i] = fmaxf(v[i], 0.f);
       }
       if (gated) v[i] = ((gate >> (c0 + i)) & 1ull) ? v[i] : 0.f;
-      ws_col[(c0 + i) * kTile] = v[i];
+      ws_col[(c0 + i) * kWsStride] = v[i];
     }
     put16(row, c0, v);
   }
@@ -317,7 +318,8 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   for (int64_t tile = (int64_t)blockIdx.x * 2 + ctx; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
     const int64_t p = tile * kTile + t;
     const bool valid = p < N;
-    float* g = ws + tile * (int64_t)(kWsRowsTc * kTile) + t;  // this point's workspace column
+    // this point's workspace column: half block t / 64, column t % 64 (a warp still writes 128 contiguous bytes)
+    float* g = ws + tile * (int64_t)(kWsRowsTc * kTile) + (t >> 6) * (kWsRowsTc * kWsStride) + (t & 63);
     // ---- inputs
     {
       const float* erow = enc + (valid ? p : 0) * enc_stride;
@@ -340,7 +342,7 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           if (!valid) v[i] = 0.f;
-          g[(rIn + c0 + i) * kTile] = v[i];
+          g[(rIn + c0 + i) * kWsStride] = v[i];
         }
         put16(row, c0, v);
       }
@@ -348,15 +350,15 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
     float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) go = __ldg(reinterpret_cast<const float4*>(dout) + p);
     const float dsigma = (valid && !(keep != nullptr && keep[p] == 0)) ? go.w : 0.f;
-    g[(rDrgb + 0) * kTile] = go.x;
-    g[(rDrgb + 1) * kTile] = go.y;
-    g[(rDrgb + 2) * kTile] = go.z;
+    g[(rDrgb + 0) * kWsStride] = go.x;
+    g[(rDrgb + 1) * kWsStride] = go.y;
+    g[(rDrgb + 2) * kWsStride] = go.z;
 #pragma unroll
-    for (int i = 3; i < 8; ++i) g[(rDrgb + i) * kTile] = 0.f;
+    for (int i = 3; i < 8; ++i) g[(rDrgb + i) * kWsStride] = 0.f;
 
     // ---- forward recompute
     run_layer<64, 32>(tmem, bar_p, phase, s_hi + oW0 * 4, s_lo + oW0 * 4, sync_id, leader);
-    const uint64_t m1 = epilogue64<true>(row, g + rH1 * kTile, 0, false);
+    const uint64_t m1 = epilogue64<true>(row, g + rH1 * kWsStride, 0, false);
     fence_before_sync();
     run_layer<16, 64>(tmem, bar_p, phase, s_hi + oW1 * 4, s_lo + oW1 * 4, sync_id, leader);
     {
@@ -367,19 +369,19 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         v[i] = valid ? __ldg(vrow + i) : 0.f;
-        g[(rC + i) * kTile] = v[i];
+        g[(rC + i) * kWsStride] = v[i];
       }
       put16(row, 0, v);
 #pragma unroll
       for (int i = 0; i < 15; ++i) v[i] = h2[1 + i];
       v[15] = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) g[(rC + 16 + i) * kTile] = v[i];
+      for (int i = 0; i < 16; ++i) g[(rC + 16 + i) * kWsStride] = v[i];
       put16(row, 16, v);
     }
     fence_before_sync();
     run_layer<64, 32>(tmem, bar_p, phase, s_hi + oW2 * 4, s_lo + oW2 * 4, sync_id, leader);
-    const uint64_t m3 = epilogue64<true>(row, g + rH3 * kTile, 0, false);
+    const uint64_t m3 = epilogue64<true>(row, g + rH3 * kWsStride, 0, false);
     fence_before_sync();
     run_layer<64, 64>(tmem, bar_p, phase, s_hi + oW3 * 4, s_lo + oW3 * 4, sync_id, leader);
     uint64_t m4 = 0;
@@ -390,7 +392,7 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         if (v[i] > 0.f) m4 |= (1ull << (c0 + i));
-        g[(rH4 + c0 + i) * kTile] = fmaxf(v[i], 0.f);
+        g[(rH4 + c0 + i) * kWsStride] = fmaxf(v[i], 0.f);
       }
     }
     // ---- backward chain
@@ -405,10 +407,10 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
     }
     fence_before_sync();
     run_layer<64, 8>(tmem, bar_p, phase, s_hi + oT4 * 4, s_lo + oT4 * 4, sync_id, leader);    // dh4 = drgb . W4
-    epilogue64<false>(row, g + rDz4 * kTile, m4, true);                      // dz4 = dh4 . [h4 > 0]
+    epilogue64<false>(row, g + rDz4 * kWsStride, m4, true);                      // dz4 = dh4 . [h4 > 0]
     fence_before_sync();
     run_layer<64, 64>(tmem, bar_p, phase, s_hi + oT3 * 4, s_lo + oT3 * 4, sync_id, leader);   // dh3 = dz4 . W3
-    epilogue64<false>(row, g + rDz3 * kTile, m3, true);                      // dz3
+    epilogue64<false>(row, g + rDz3 * kWsStride, m3, true);                      // dz3
     fence_before_sync();
     run_layer<16, 64>(tmem, bar_p, phase, s_hi + oT2 * 4, s_lo + oT2 * 4, sync_id, leader);   // dgeo = (dz3 . W2)[16:31]
     {
@@ -418,12 +420,12 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 #pragma unroll
       for (int i = 0; i < 15; ++i) v[1 + i] = dg[i];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) g[(rDh2 + i) * kTile] = v[i];
+      for (int i = 0; i < 16; ++i) g[(rDh2 + i) * kWsStride] = v[i];
       put16(row, 0, v);  // A = dh2, K = 16
     }
     fence_before_sync();
     run_layer<64, 16>(tmem, bar_p, phase, s_hi + oT1 * 4, s_lo + oT1 * 4, sync_id, leader);   // dh1 = dh2 . W1
-    epilogue64<false>(row, g + rDz1 * kTile, m1, true);                      // dz1
+    epilogue64<false>(row, g + rDz1 * kWsStride, m1, true);                      // dz1
     fence_before_sync();
     run_layer<32, 64>(tmem, bar_p, phase, s_hi + oT0 * 4, s_lo + oT0 * 4, sync_id, leader);   // d_enc = dz1 . W0
 #pragma unroll
@@ -479,7 +481,7 @@ __device__ __forceinline__ void prefetch_pair(const float* __restrict__ base, co
       const int r8 = i & 7, rest = i >> 3;
       const int chunk = rest % (kHalf / 4), rg = rest / (kHalf / 4);
       const int r = (is_n ? pr.n_row : pr.m_row) + rg * 8 + r8;
-      reg[s] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * kTile) + chunk);
+      reg[s] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * kWsStride) + chunk);
     }
   }
 }
@@ -537,7 +539,7 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
                              {rH4, rDrgb, 8, cW4}};
   const int64_t n_half = ((N + kTile - 1) / kTile) * 2;
   const int64_t G = gridDim.x;
-  auto base_of = [&](int64_t hh) { return ws + (hh >> 1) * (int64_t)(kWsRowsTc * kTile) + (hh & 1) * kHalf; };
+  auto base_of = [&](int64_t hh) { return ws + (hh >> 1) * (int64_t)(kWsRowsTc * kTile) + (hh & 1) * (kWsRowsTc * kWsStride); };
   // Two register sets: the set consumed at step k is refilled at once with the loads of step k + 2, so global
   // loads have two full pair-times (several microseconds) to land.  A loop iteration covers two half tiles
   // = 10 steps, which keeps the set <-> step mapping static.

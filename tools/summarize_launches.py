@@ -23,10 +23,10 @@ for d in rows.values():
             a[k].append(v)
 tot = sum(sum(a['gpu__time_duration.sum']) for a in agg.values())
 metrics = [m for m in next(iter(agg.values())).keys() if m != 'gpu__time_duration.sum']
-print(f"| kernel | launches | total us | share | " + " | ".join(metrics) + " |")
+print("| kernel | launches | total us | share |" + "".join(f" {m} (mean per launch) |" for m in metrics))
 print("|---|---:|---:|---:|" + "---:|" * len(metrics))
 for name, a in sorted(agg.items(), key=lambda kv: -sum(kv[1]['gpu__time_duration.sum'])):
     t = a['gpu__time_duration.sum']
-    extra = " | ".join(f"{sum(a[m]) / max(1, len(a[m])):.3g}" for m in metrics)
-    print(f"| `{name}` | {len(t)} | {sum(t):.1f} | {sum(t) / tot:.1%} | {extra} |")
+    extra = "".join(f" {sum(a[m]) / max(1, len(a[m])):.3g} |" for m in metrics)  # mean per launch
+    print(f"| `{name}` | {len(t)} | {sum(t):.1f} | {sum(t) / tot:.1%} |{extra}")
 print(f"\ntotal {tot:.1f} us over {sum(len(a['gpu__time_duration.sum']) for a in agg.values())} launches")
