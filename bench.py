@@ -158,8 +158,11 @@ def workload_config(args, n_points):
 # ------------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------------
-def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False):
-    """BASELINE configs[2]/[3] shape: full coarse+fine render + loss + backward + RAdam on synthetic rays."""
+def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, rank=0, world=1):
+    """BASELINE configs[2]/[3] shape: full coarse+fine render + loss + backward + RAdam on synthetic rays.
+    With ``dist`` (N > 1): every rank renders its own n_rand rays, gradients are summed over ranks with one flat
+    all-reduce per parameter group (hn_b200.dp.GradSync) and 1/world is applied inside the fused RAdam kernel;
+    returns whole-job rays/s."""
     from embedding.hash_encoding import HashEmbedder
     from embedding.spherical_harmonic import SHEncoder
     from models import NeRFSmall
@@ -172,7 +175,7 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False):
     coarse, fine, sh = mk(), mk(), SHEncoder()
     opt = RAdam([{"params": list(coarse.parameters()) + list(fine.parameters()), "weight_decay": 1e-6},
                  {"params": list(emb.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
-    g = torch.Generator(device=dev).manual_seed(1)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)  # identical init (seed 0 above), distinct rays per rank
     o = torch.tensor([0., 0., 4.], device=dev) + 0.1 * torch.randn(n_rand, 3, device=dev, generator=g)
     d = -o / o.norm(dim=-1, keepdim=True) + 0.2 * torch.randn(n_rand, 3, device=dev, generator=g)
     rays = torch.cat([o, d, torch.full((n_rand, 1), 2., device=dev), torch.full((n_rand, 1), 6., device=dev),
@@ -198,6 +201,10 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False):
             step()
     else:
         from loss import total_variation_loss
+        sync = None
+        if dist is not None:
+            from hn_b200.dp import GradSync
+            sync = GradSync(list(emb.parameters()) + list(coarse.parameters()) + list(fine.parameters()))
 
         def step():  # the statements of the reference's loop body, run_nerf.py:608-642
             ret = render_fn(rays)
@@ -207,10 +214,14 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False):
                                           emb.log2_hashmap_size, n_levels=emb.n_levels) for i in range(emb.n_levels))
             loss = loss + 1e-6 * tv
             loss.backward()
+            if sync is not None:
+                sync.all_reduce()
+                sync.wait()
+                opt.grad_scale = sync.grad_scale
             opt.step()
 
-    ms = time_loop(step, steps, warmup) / steps
-    return n_rand / ms * 1e3, ms
+    ms = time_loop(step, steps, warmup, dist) / steps
+    return world * n_rand / ms * 1e3, ms
 
 
 def inference_frame_extra(dev, H=800, W=800):
@@ -408,6 +419,18 @@ def run_ours(args):
     e2e = {"value": round(world * n / e2e_ms / 1e3, 2), "unit": "Msamples/s", "h2d_bytes_per_step": n * 12,
            "d2h_bytes_per_step": L * 4, "ms_per_step": round(e2e_ms, 3), "chunks": n_chunks, "api": api}
 
+    # ---- N > 1: the data-parallel training step (every rank takes part)
+    extra = {}
+    if world > 1 and not args.no_extra:
+        x_host = x_dev = x_bufs = None
+        out_holder.clear()
+        torch.cuda.empty_cache()
+        rps, ms = train_step_extra(dev, 8192, steps=10, warmup=3, dist=dist, rank=rank, world=world)
+        extra["train_rays_per_s_nrand8192_per_rank_dp"] = round(rps, 1)
+        extra["train_ms_per_step_nrand8192_per_rank_dp"] = round(ms, 3)
+        extra["train_step"] = ("data parallel: 8192 rays per rank, render_rays 64+128, mse+sparsity+16 TV terms, "
+                               "backward, flat gradient all-reduce (GradSync), RAdam with 1/world folded in; eager")
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -415,7 +438,6 @@ def run_ours(args):
         return
 
     # ---- extras (rank 0 only, N=1 only): other table sizes, training step
-    extra = {}
     if world == 1 and not args.no_extra:
         x_host = x_dev = x_bufs = None  # release the e2e buffers before the extra workloads
         for t_log2 in (14, 22):
