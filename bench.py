@@ -152,7 +152,10 @@ def workload_config(args, n_points):
             "points_per_step_per_gpu": n_points, "log2_hashmap_size": args.log2T,
             "l2": "inputs larger than L2 (x 201 MB + dY 2.1 GB + features 2.1 GB per step); the 64 MiB table stays "
                   "L2-resident across steps, as in steady-state training",
-            "parallelism": f"dp{args.gpus} (points sharded, table gradient all-reduced)" if args.gpus > 1 else "single"}
+            "parallelism": (f"dp{args.gpus} (points sharded; table gradient all-reduced "
+                            + ("in 4 level buckets, each overlapping the next bucket's scatter" if args.bucket_overlap
+                               else "once after the scatter") + ")")
+            if args.gpus > 1 else "single"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -292,15 +295,29 @@ def run_ours(args):
     def bwd():
         ops.hash_encode_backward_sorted(out_holder["xs4"], dy, box, res, L, F, log2T, dflat)
 
+    reducer, buckets = None, []
+    if dist is not None and args.bucket_overlap:
+        from hn_b200.dp import BucketedTableReducer
+        reducer = BucketedTableReducer(L)
+        buckets = BucketedTableReducer.buckets(L, 4)
+
     def step():
         # what HashEmbedder.forward + autograd backward launch for this many points: counting sort by grid
         # cell, sorted gather, zero-grad, warp-aggregated scatter (+ the DP all-reduce)
         dflat.zero_()
         sort()
         fwd()
-        bwd()
-        if dist is not None:
+        if dist is None:
+            bwd()
+        elif reducer is None:
+            bwd()
             dist.all_reduce(dflat)
+        else:
+            # level buckets: the all-reduce of bucket b runs on a side stream while bucket b+1 is scattered
+            for b, e in buckets:
+                ops.hash_encode_backward_sorted(out_holder["xs4"], dy, box, res, L, F, log2T, dflat, levels=(b, e))
+                reducer.reduce_levels(dflat, b, e)
+            reducer.wait()
 
     # ---- headline: device-resident inputs
     clocks = ClockSampler(local)
@@ -506,6 +523,9 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="1 = upload each step's points one step ahead (double buffer); >1 = split one step into "
                          "geometric pieces and overlap piece c+1's upload with piece c's compute")
+    ap.add_argument("--bucket-overlap", action="store_true",
+                    help="N > 1: all-reduce the table gradient in 4 level buckets overlapped with the scatter instead "
+                         "of once after it (measured slower: splitting the scatter costs more than the overlap hides)")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -31,6 +31,7 @@ SIGNATURES = {
     "hn_hash_sort_points": (_i, [_p, _p, _l, _i, _p, _p, _p]),
     "hn_hash_encode_fwd_sorted": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _p]),
     "hn_hash_encode_bwd_sorted": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
+    "hn_hash_encode_bwd_sorted_levels": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _i, _i, _p]),
     "hn_sh_encode": (_i, [_p, _l, _i, _p, _p]),
     "hn_mlp_fwd": (_i, [_p, _l, _p, _l, _l, _p, _p, _l, _p, _p]),
     "hn_mlp_bwd_workspace_bytes": (_l, [_l]),

@@ -113,6 +113,62 @@ class GradSync:
         self._works = []
 
 
+class BucketedTableReducer:
+    """All-reduce of the hash-table gradient in level buckets, overlapped with the scatter.
+
+    The flat gradient ``[L * 2^T * F]`` is level-major, so the levels ``[b, e)`` are the contiguous slice
+    ``flat[b * slab : e * slab]``.  The caller scatters bucket after bucket on its compute stream
+    (``ops.hash_encode_backward_sorted(..., levels=(b, e))``) and calls :meth:`reduce_levels` after each: the summed
+    all-reduce of that slice is enqueued on a side stream behind an event, so it runs while the next bucket is
+    being scattered.  :meth:`wait` joins the side stream.  On CPU tensors (gloo, the unit tests) the collectives
+    are asynchronous works joined by :meth:`wait`.
+    """
+
+    def __init__(self, n_levels: int, group=None):
+        self.n_levels = int(n_levels)
+        self.group = group
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.grad_scale = 1.0 / self.world_size
+        self._stream: Optional[torch.cuda.Stream] = None
+        self._works = []
+        self.calls_last = 0
+
+    @staticmethod
+    def buckets(n_levels: int, levels_per_bucket: int = 4) -> List[Tuple[int, int]]:
+        """[(begin, end)] covering [0, n_levels) in runs of ``levels_per_bucket`` (the last may be shorter)."""
+        step = max(1, int(levels_per_bucket))
+        return [(b, min(b + step, n_levels)) for b in range(0, n_levels, step)]
+
+    def reduce_levels(self, flat: torch.Tensor, begin: int, end: int) -> None:
+        if not (0 <= begin <= end <= self.n_levels):
+            raise ValueError(f"level range [{begin}, {end}) outside [0, {self.n_levels})")
+        if flat.numel() % self.n_levels:
+            raise ValueError("flat gradient length is not a multiple of the level count")
+        if self.world_size == 1 or begin == end:
+            return
+        slab = flat.numel() // self.n_levels
+        piece = flat.view(-1)[begin * slab:end * slab]
+        self.calls_last += 1
+        if piece.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=piece.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(piece.device))   # the bucket's scatter has been enqueued
+            self._stream.wait_event(ev)
+            with torch.cuda.stream(self._stream):
+                dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self._works.append(dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self) -> None:
+        if self._stream is not None:
+            torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        self.calls_last = 0
+
+
 def all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
     """Inference: concatenate per-rank row blocks (``counts[r]`` rows from rank r) on every rank."""
     world = dist.get_world_size(group)

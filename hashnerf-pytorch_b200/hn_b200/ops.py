@@ -175,12 +175,18 @@ def hash_encode_forward_sorted(xs4, tables_flat, bbox6, resolutions, L, F, log2T
     return out, keep
 
 
-def hash_encode_backward_sorted(xs4, dy, bbox6, resolutions, L, F, log2T, dtables_flat):
+def hash_encode_backward_sorted(xs4, dy, bbox6, resolutions, L, F, log2T, dtables_flat, levels=None):
+    """``levels = (begin, end)`` restricts the scatter to that level range (gradient buckets, see dp.py)."""
     dev = _need_cuda(xs4, dy, bbox6, resolutions, dtables_flat)
     dy = _f32c(dy)
     with _on(dev):
-        _lib.call("hn_hash_encode_bwd_sorted", xs4.data_ptr(), dy.data_ptr(), bbox6.data_ptr(),
-                  resolutions.data_ptr(), xs4.shape[0], L, F, log2T, dtables_flat.data_ptr(), _stream())
+        if levels is None:
+            _lib.call("hn_hash_encode_bwd_sorted", xs4.data_ptr(), dy.data_ptr(), bbox6.data_ptr(),
+                      resolutions.data_ptr(), xs4.shape[0], L, F, log2T, dtables_flat.data_ptr(), _stream())
+        else:
+            _lib.call("hn_hash_encode_bwd_sorted_levels", xs4.data_ptr(), dy.data_ptr(), bbox6.data_ptr(),
+                      resolutions.data_ptr(), xs4.shape[0], L, F, log2T, dtables_flat.data_ptr(), int(levels[0]),
+                      int(levels[1]), _stream())
 
 
 # Points are re-ordered by grid cell before encoding when there are at least this many of them (the sort

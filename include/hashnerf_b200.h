@@ -89,6 +89,14 @@ HN_API int hn_hash_encode_fwd_sorted(const float* xs4, const float* tables, cons
 HN_API int hn_hash_encode_bwd_sorted(const float* xs4, const float* dy, const float* bbox,
                                      const float* resolutions, int64_t N, int L, int F, int log2T, float* dtables,
                                      void* stream);
+/* The scatter of hn_hash_encode_bwd_sorted restricted to levels [level_begin, level_end): dy and dtables are the
+ * FULL [N, L*F] / [L, 2^log2T, F] arrays.  Calling it over a partition of [0, L) equals one full call; it exists so
+ * that a data-parallel caller can all-reduce the table-gradient slab of one level bucket while the next bucket is
+ * still being scattered (hn_b200/dp.py: BucketedTableReducer).  Ranges aligned to 4 levels keep the
+ * kernel's 4-levels-per-thread mapping; other ranges run with fewer levels per thread. */
+HN_API int hn_hash_encode_bwd_sorted_levels(const float* xs4, const float* dy, const float* bbox,
+                                            const float* resolutions, int64_t N, int L, int F, int log2T,
+                                            float* dtables, int level_begin, int level_end, void* stream);
 
 /* ---- (a7) spherical harmonics : embedding/spherical_harmonic.py:65-103 ------------------------- */
 /* dirs [N,3] -> out [N, degree^2], 1 <= degree <= 5. */

@@ -53,6 +53,25 @@ def _worker(rank, world, port, q):
         dist.all_reduce(covered)
         assert torch.all(covered == 1)
 
+        # level-bucketed reduction of the flat table gradient: every bucket summed exactly once, nothing else touched
+        L_, slab = 6, 10
+        tg = torch.arange(L_ * slab, dtype=torch.float32) * (rank + 1)
+        red = dp.BucketedTableReducer(L_)
+        bk = dp.BucketedTableReducer.buckets(L_, 4)
+        assert bk == [(0, 4), (4, 6)]
+        red.reduce_levels(tg, *bk[0])
+        red.wait()
+        want = torch.arange(L_ * slab, dtype=torch.float32)
+        assert torch.equal(tg[:4 * slab], 3 * want[:4 * slab]) and torch.equal(tg[4 * slab:], (rank + 1) * want[4 * slab:])
+        red.reduce_levels(tg, *bk[1])
+        red.wait()
+        assert torch.equal(tg, 3 * want) and red.grad_scale == 0.5
+        try:
+            red.reduce_levels(tg, 2, 9)
+            raise AssertionError("out-of-range bucket accepted")
+        except ValueError:
+            pass
+
         # inference gather of ragged row blocks
         counts = [dp.shard_range(11, r, world)[1] - dp.shard_range(11, r, world)[0] for r in range(world)]
         local = torch.arange(s, e, dtype=torch.float32)[:, None].repeat(1, 3)

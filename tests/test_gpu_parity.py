@@ -226,6 +226,32 @@ def test_hash_encode_cell_boundaries_bit_exact(bbox, coherent):
         bit_equal(hashed[l], whash)
 
 
+@pytest.mark.parametrize("parts", [[(0, 4), (4, 8), (8, 12), (12, 16)], [(0, 16)], [(0, 6), (6, 7), (7, 16)],
+                                   [(0, 8), (8, 8), (8, 16)]])
+def test_hash_encode_backward_level_buckets(parts):
+    """hn_hash_encode_bwd_sorted_levels over a partition of the levels == one full scatter (the gradient buckets
+    of the data-parallel path), including ranges that are not multiples of the 4-levels-per-thread mapping."""
+    from hn_b200 import ops
+    log2T, n = 14, 30_000
+    emb, tables = make_embedder(cases.BBOX_ODD, log2T)
+    x = g32(cases.points_in_box(n, cases.BBOX_ODD, seed=4242))
+    dy = g32(np.random.RandomState(6).randn(n, 32).astype(np.float32))
+    box, res = emb._geometry(torch.device(DEV))
+    xs4 = ops.hash_sort_points(x, box, 32)
+    full = torch.zeros(16 << log2T, 2, device=DEV)
+    ops.hash_encode_backward_sorted(xs4, dy, box, res, 16, 2, log2T, full)
+    got = torch.zeros_like(full)
+    for b, e in parts:
+        before = got.clone()
+        ops.hash_encode_backward_sorted(xs4, dy, box, res, 16, 2, log2T, got, levels=(b, e))
+        changed = (got != before).view(16, -1).any(dim=1).cpu().numpy()
+        assert not changed[:b].any() and not changed[e:].any(), "a bucket wrote outside its levels"
+    scale = full.abs().max().item()
+    assert (got - full).abs().max().item() <= GRAD_RTOL * scale
+    with pytest.raises(RuntimeError):
+        ops.hash_encode_backward_sorted(xs4, dy, box, res, 16, 2, log2T, got, levels=(5, 17))
+
+
 @pytest.mark.parametrize("n", [0, 1, 255, 257])
 def test_hash_encode_ragged_and_empty(n):
     emb, tables = make_embedder(cases.BBOX_ODD, 10)
