@@ -131,7 +131,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 1 << 16
+    n = 1 << 19
     steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
     v, ms, cores = cpu_hash_encode_fwd_bwd(n, args.log2T, steps, warmup)
     sample = f"{n} of the 2^24 points per step (oracle port of hash_encoding.py fwd + autograd bwd, torch CPU fp32)"
@@ -495,10 +495,10 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        n_cpu = 1 << 17
-        v, ms, cores = cpu_hash_encode_fwd_bwd(n_cpu, log2T, steps=2, warmup=1)
+        n_cpu = 1 << 20
+        v, ms, cores = cpu_hash_encode_fwd_bwd(n_cpu, log2T, steps=3, warmup=1)
         cpu = {"value": round(v, 4), "unit": "Msamples/s", "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} of the 2^24 points, 2 timed passes after 1 warm-up ({ms:.0f} ms/pass), oracle port "
+               "sample": f"{n_cpu} of the 2^24 points, 3 timed passes after 1 warm-up ({ms:.0f} ms/pass), oracle port "
                          "of the reference's PyTorch encoder fwd + autograd bwd"}
 
     line = {"metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,

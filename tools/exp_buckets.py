@@ -16,3 +16,6 @@ for parts in ([(0, 16)], [(0, 8), (8, 16)], [(0, 4), (4, 8), (8, 12), (12, 16)])
         for b, e in parts:
             ops.hash_encode_backward_sorted(xs4, dy, box, res, 16, 2, 19, dt, levels=(b, e))
     print(json.dumps({"parts": len(parts), "bwd_ms": round(timeit(f, 10), 3)}), flush=True)
+for b in range(0, 16, 2):
+    f = lambda: ops.hash_encode_backward_sorted(xs4, dy, box, res, 16, 2, 19, dt, levels=(b, b + 2))
+    print(json.dumps({"levels": [b, b + 2], "bwd_ms": round(timeit(f, 10), 3)}), flush=True)
