@@ -227,7 +227,7 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, r
     return world * n_rand / ms * 1e3, ms
 
 
-def inference_frame_extra(dev, H=800, W=800):
+def inference_frame_extra(dev, H=800, W=800, dist=None):
     """BASELINE configs[4] shape: one 800x800 frame = 640 000 rays x (64 + 128) samples, perturb 0, no_grad."""
     from embedding.hash_encoding import HashEmbedder
     from embedding.spherical_harmonic import SHEncoder
@@ -243,13 +243,27 @@ def inference_frame_extra(dev, H=800, W=800):
     K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
     c2w = torch.tensor([[1, 0, 0, 0.0], [0, 1, 0, 0.0], [0, 0, 1, 4.0]], device=dev)
 
-    def frame():
-        with torch.no_grad():
-            render(H, W, K, chunk=1024 * 32, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True, network_fn=coarse,
-                   network_fine=fine, network_query_fn=qfn, N_samples=64, N_importance=128, embed_fn=emb, perturb=0.,
-                   raw_noise_std=0., white_bkgd=True)
+    kw = dict(ndc=False, near=2., far=6., use_viewdirs=True, network_fn=coarse, network_fine=fine,
+              network_query_fn=qfn, N_samples=64, N_importance=128, embed_fn=emb, perturb=0., raw_noise_std=0.,
+              white_bkgd=True)
 
-    ms = time_loop(frame, 3, 1) / 3
+    if dist is None:
+        def frame():
+            with torch.no_grad():
+                render(H, W, K, chunk=1024 * 32, c2w=c2w, **kw)
+    else:
+        # SURVEY 8e inference partition: a contiguous range of the frame's rays per rank, one all-gather at the end
+        from hn_b200.dp import render_image_sharded
+
+        def render_fn(o, d):
+            rgb, depth, acc, _extras = render(H, W, K, chunk=1024 * 32, rays=(o, d), **kw)
+            return rgb, depth, acc
+
+        def frame():
+            with torch.no_grad():
+                render_image_sharded(H, W, K, c2w, render_fn)
+
+    ms = time_loop(frame, 3, 1, dist) / 3
     return ms
 
 
@@ -447,6 +461,9 @@ def run_ours(args):
         extra["train_ms_per_step_nrand8192_per_rank_dp"] = round(ms, 3)
         extra["train_step"] = ("data parallel: 8192 rays per rank, render_rays 64+128, mse+sparsity+16 TV terms, "
                                "backward, flat gradient all-reduce (GradSync), RAdam with 1/world folded in; eager")
+        ms = inference_frame_extra(dev, dist=dist)
+        extra["inference_800x800_ms_per_frame_rays_sharded"] = round(ms, 2)
+        extra["inference_800x800_mrays_per_s_rays_sharded"] = round(0.64 / ms * 1e3, 2)
 
     if rank != 0:
         if dist is not None:

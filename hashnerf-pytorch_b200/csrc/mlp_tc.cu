@@ -662,6 +662,8 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
 
 }  // namespace tc
 
+int g_mlp_fwd_one_cta = 0;
+
 int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
                const float* weights, const uint8_t* keep, int64_t N, float* out, int aligned, cudaStream_t stream) {
   static thread_local int done_dev = -1;
@@ -669,14 +671,16 @@ int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail((int)e, "cudaGetDevice");
   if (done_dev != dev) {
-    e = cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kFwdSmemBytes);
+    e = cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_fwd_kernel)");
     done_dev = dev;
   }
   const int64_t tiles = (N + tc::kTile - 1) / tc::kTile;
   const int64_t cap = (int64_t)sm_count() * 2;
   const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-  tc::mlp_tc_fwd_kernel<<<grid, tc::kTile, tc::kFwdSmemBytes, stream>>>(enc, enc_stride, views, views_stride,
+  // profiling knob (hn_set_tuning "mlp_fwd_one_cta"): pad the dynamic shared memory so that only one CTA fits per SM
+  const size_t smem_bytes = g_mlp_fwd_one_cta ? (size_t)160 * 1024 : tc::kFwdSmemBytes;
+  tc::mlp_tc_fwd_kernel<<<grid, tc::kTile, smem_bytes, stream>>>(enc, enc_stride, views, views_stride,
                                                                        pts_per_view, weights, keep, N, out, aligned);
   return check_launch("mlp_tc_fwd_kernel");
 }

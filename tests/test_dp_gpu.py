@@ -89,6 +89,26 @@ def _worker(rank, world, port, q):
         other = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(other, flat)
         assert all(torch.equal(o, other[0]) for o in other), "ranks diverged after the optimizer step"
+        # inference partition: rays of a frame sharded over ranks + all-gather == the frame rendered by one process
+        from run_nerf_helpers import render, run_network
+        H, W = 20, 24
+        focal = 0.5 * W / np.tan(0.5 * 0.69)
+        K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+        c2w = torch.tensor([[1, 0, 0, 0.0], [0, 1, 0, 0.0], [0, 0, 1, 2.5]], device=dev)
+        qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb2, embeddirs_fn=sh2)
+        kw = dict(ndc=False, near=1., far=4., use_viewdirs=True, network_fn=nets2[0], network_fine=nets2[1],
+                  network_query_fn=qfn, N_samples=16, N_importance=16, embed_fn=emb2, perturb=0., raw_noise_std=0.,
+                  white_bkgd=True)
+
+        def render_fn(o, d):
+            rgb, depth, acc, _ = render(H, W, K, chunk=128, rays=(o, d), **kw)
+            return rgb, depth, acc
+        with torch.no_grad():
+            rgb_s, depth_s, acc_s = dp.render_image_sharded(H, W, K, c2w, render_fn)
+            rgb_1, depth_1, acc_1, _ = render(H, W, K, chunk=4096, c2w=c2w, **kw)
+        assert rgb_s.shape == (H, W, 3) and depth_s.shape == (H, W)
+        for a, b, what in ((rgb_s, rgb_1, "rgb"), (depth_s, depth_1, "depth"), (acc_s, acc_1, "acc")):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6, equal_nan=True), f"sharded frame differs: {what}"
         q.put((rank, "ok"))
     except Exception as exc:  # noqa: BLE001
         import traceback
