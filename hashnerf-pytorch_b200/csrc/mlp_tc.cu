@@ -456,13 +456,16 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 constexpr int kHalf = 64;
 constexpr uint32_t cW0 = 0, cW1 = 32, cW2 = 48, cW3 = 80, cW4 = 144;  // accumulator columns
 constexpr size_t kWeightBufBytes = (size_t)4 * 64 * kHalf * sizeof(float);  // (M_hi | M_lo | N_hi | N_lo) = 64 KB
+constexpr size_t kWeightAlignPad = 1024;  // slack so that the staging area can start on a 1024-byte boundary
 
-// Staging of one operand pair for a 64-point half tile.  Slot s of thread t covers float4 number s*128 + t of
-// the pair: the first 1024 belong to the 64 M-side rows, the rest to the N-side rows.  Within an operand,
-// consecutive indices walk (row % 8, 16-byte chunk, row group) so that the 8 lanes of one chunk fill one
-// 128-byte core matrix (conflict-free STS.128) while reading 64 contiguous bytes per row.
+// Staging of one operand pair for a 64-point half tile.  The rows of one operand are consecutive workspace rows of
+// 64 floats, i.e. ONE contiguous range, so thread t's slot s simply takes float4 number s*256 + t of the pair
+// (the first 64*16 belong to the M-side rows, the rest to the N-side rows): a quarter warp reads one full
+// 128-byte line.  In shared memory an operand is two 128-byte-swizzled K-major blocks (points 0..31 and 32..63
+// of the half tile); the 8 lanes of a quarter warp hold the 8 chunks of one row and the XOR with the row index
+// spreads them over all 32 banks (conflict-free STS.128).
 constexpr int kWThreads = 256;  // threads of the weight-gradient kernel
-constexpr int kSlots = 8;    // (64 + 64 rows) * 16 chunks / 256 threads
+constexpr int kSlots = 8;       // (64 + 64 rows) * 16 float4 / 256 threads
 
 struct PairDesc {
   int m_row, n_row, n_rows;
@@ -471,18 +474,13 @@ struct PairDesc {
 
 __device__ __forceinline__ void prefetch_pair(const float* __restrict__ base, const PairDesc& pr, float4 (&reg)[kSlots]) {
   const int total = (64 + pr.n_rows) * (kHalf / 4);
+  const float4* m_src = reinterpret_cast<const float4*>(base + (int64_t)pr.m_row * kWsStride);
+  const float4* n_src = reinterpret_cast<const float4*>(base + (int64_t)pr.n_row * kWsStride) - 64 * (kHalf / 4);
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) {
     const int idx = s * kWThreads + threadIdx.x;
     reg[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx < total) {
-      const bool is_n = idx >= 64 * (kHalf / 4);
-      const int i = is_n ? idx - 64 * (kHalf / 4) : idx;
-      const int r8 = i & 7, rest = i >> 3;
-      const int chunk = rest % (kHalf / 4), rg = rest / (kHalf / 4);
-      const int r = (is_n ? pr.n_row : pr.m_row) + rg * 8 + r8;
-      reg[s] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * kWsStride) + chunk);
-    }
+    if (idx < total) reg[s] = __ldg((idx >= 64 * (kHalf / 4) ? n_src : m_src) + idx);
   }
 }
 
@@ -495,9 +493,9 @@ __device__ __forceinline__ void store_pair(const PairDesc& pr, const float4 (&re
     if (idx < total) {
       const bool is_n = idx >= 64 * (kHalf / 4);
       const int i = is_n ? idx - 64 * (kHalf / 4) : idx;
-      const int r8 = i & 7, rest = i >> 3;
-      const int chunk = rest % (kHalf / 4), rg = rest / (kHalf / 4);
-      const int off = (rg * (kHalf / 4) + chunk) * 32 + r8 * 4;
+      const int row = i >> 4, kb = (i >> 3) & 1, j = i & 7;     // 16 float4 per row: 2 blocks of 8 chunks
+      const int rows = is_n ? pr.n_rows : 64;
+      const int off = kb * (rows * 32) + (row >> 3) * 256 + (row & 7) * 32 + ((j ^ (row & 7)) << 2);
       uint32_t h[4], l[4];
       split_tf32(reg[s].x, h[0], l[0]);
       split_tf32(reg[s].y, h[1], l[1]);
@@ -516,7 +514,9 @@ __device__ __forceinline__ void store_pair(const PairDesc& pr, const float4 (&re
 template <int NBUF>
 __global__ void __launch_bounds__(kWThreads, NBUF == 1 ? 2 : 1)
 mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restrict__ dweights, int ablate) {
-  extern __shared__ __align__(128) float smem[];
+  extern __shared__ __align__(128) float smem_raw[];
+  // swizzle atoms are addressed by absolute shared-memory address bits: align the staging area to 1024 bytes
+  float* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) / 4;
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -577,21 +577,28 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
       if (t == 0) {
         fence_after_sync();
         const uint32_t idesc = make_idesc(64, pr.n_rows);
-        constexpr uint64_t kHiBits =
-            ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(((kHalf / 4) * 128) >> 4) << 32) | (1ull << 46);
-        const uint64_t m_hi = kHiBits | (uint64_t)((smem_u32(Mhi) >> 4) & 0x3FFF);
-        const uint64_t m_lo = kHiBits | (uint64_t)((smem_u32(Mlo) >> 4) & 0x3FFF);
-        const uint64_t n_hi = kHiBits | (uint64_t)((smem_u32(Nhi) >> 4) & 0x3FFF);
-        const uint64_t n_lo = kHiBits | (uint64_t)((smem_u32(Nlo) >> 4) & 0x3FFF);
+        const uint64_t m_hi = make_sdesc_sw128(smem_u32(Mhi), 1024), m_lo = make_sdesc_sw128(smem_u32(Mlo), 1024);
+        const uint64_t n_hi = make_sdesc_sw128(smem_u32(Nhi), 1024), n_lo = make_sdesc_sw128(smem_u32(Nlo), 1024);
+        // K step s: block s / 4 (rows * 128 bytes further), 32 bytes per step inside the swizzled row
+        const uint64_t m_blk = (uint64_t)((64 * 128) >> 4), n_blk = (uint64_t)((pr.n_rows * 128) >> 4);
         const uint32_t first = ((fresh >> i) & 1u) ? 0u : 1u;
         const uint32_t d = tmem + pr.col;
         if (!(ablate & 2)) {
 #pragma unroll
-          for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_lo + 16 * s, n_hi + 16 * s, idesc, s ? 1u : first);
+          for (int s = 0; s < kHalf / 8; ++s) {
+            const uint64_t mo = (s >> 2) * m_blk + 2 * (s & 3), no = (s >> 2) * n_blk + 2 * (s & 3);
+            umma_ss(d, m_lo + mo, n_hi + no, idesc, s ? 1u : first);
+          }
 #pragma unroll
-          for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_hi + 16 * s, n_lo + 16 * s, idesc, 1u);
+          for (int s = 0; s < kHalf / 8; ++s) {
+            const uint64_t mo = (s >> 2) * m_blk + 2 * (s & 3), no = (s >> 2) * n_blk + 2 * (s & 3);
+            umma_ss(d, m_hi + mo, n_lo + no, idesc, 1u);
+          }
 #pragma unroll
-          for (int s = 0; s < kHalf / 8; ++s) umma_ss(d, m_hi + 16 * s, n_hi + 16 * s, idesc, 1u);
+          for (int s = 0; s < kHalf / 8; ++s) {
+            const uint64_t mo = (s >> 2) * m_blk + 2 * (s & 3), no = (s >> 2) * n_blk + 2 * (s & 3);
+            umma_ss(d, m_hi + mo, n_hi + no, idesc, 1u);
+          }
         }
         umma_commit(&bars[b]);
       }
@@ -705,10 +712,10 @@ int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t
                              (int)tc::kDeltaSmemBytes);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_delta_kernel)");
     e = cudaFuncSetAttribute(tc::mlp_tc_bwd_weight_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)tc::kWeightBufBytes);
+                             (int)(tc::kWeightBufBytes + tc::kWeightAlignPad));
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_weight_kernel<1>)");
     e = cudaFuncSetAttribute(tc::mlp_tc_bwd_weight_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(2 * tc::kWeightBufBytes));
+                             (int)(2 * tc::kWeightBufBytes + tc::kWeightAlignPad));
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_weight_kernel<2>)");
     done_dev = dev;
   }
@@ -728,10 +735,10 @@ int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t
     const int64_t cap = (int64_t)sm_count() * (nbuf == 1 ? 2 : 1);
     const unsigned grid = (unsigned)(halves < cap ? halves : cap);
     if (nbuf == 1)
-      tc::mlp_tc_bwd_weight_kernel<1><<<grid, tc::kWThreads, tc::kWeightBufBytes, stream>>>(N, workspace, dweights,
+      tc::mlp_tc_bwd_weight_kernel<1><<<grid, tc::kWThreads, tc::kWeightBufBytes + tc::kWeightAlignPad, stream>>>(N, workspace, dweights,
                                                                                            g_mlp_dw_ablate);
     else
-      tc::mlp_tc_bwd_weight_kernel<2><<<grid, tc::kWThreads, 2 * tc::kWeightBufBytes, stream>>>(
+      tc::mlp_tc_bwd_weight_kernel<2><<<grid, tc::kWThreads, 2 * tc::kWeightBufBytes + tc::kWeightAlignPad, stream>>>(
           N, workspace, dweights, g_mlp_dw_ablate);
     return check_launch("mlp_tc_bwd_weight_kernel");
   }

@@ -71,6 +71,18 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo, uin
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// 128-byte-swizzled K-major matrix descriptor: a row holds 32 fp32 K elements (128 B), 8 rows form a 1024-byte
+// atom whose 16-byte chunks are XOR-ed with the row index (address bits [4,7) ^= bits [7,10)), SBO = byte step
+// between 8-row atoms; LBO is not used by swizzled K-major layouts (set to 1 as CUTLASS does).  Atoms must be
+// 1024-byte aligned.  A K step of 8 elements inside the 128-byte row is +32 bytes on the start address.
+__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// placement (in floats) of element (r, k), k < 32, inside a swizzled [R x 32] block
+__host__ __device__ constexpr int sw128(int r, int k) {
+  return (r >> 3) * 256 + (r & 7) * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3));
+}
 // canonical no-swizzle K-major placement (in floats) of element (r, k) of an [R x K] fp32 operand:
 // 8x4 core matrices of 128 contiguous bytes, K-adjacent core matrices 128 B apart, row groups (K/4)*128 B apart
 __host__ __device__ constexpr int canon(int r, int k, int K) {
