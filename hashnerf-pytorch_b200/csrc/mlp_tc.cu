@@ -99,6 +99,58 @@ __device__ __forceinline__ void run_layer(uint32_t tmem, uint64_t* bar, uint32_t
   fence_after_sync();
 }
 
+// Per-point inputs of one tile, loaded one tile ahead so that the global-load latency hides behind the layer
+// chain of the current tile: the 32 hash features, the 16 SH coefficients of the point's ray, the keep flag.
+struct TileInputs {
+  float e[2][16];
+  float v[16];
+  uint8_t keep;
+};
+
+__device__ __forceinline__ void load_tile_inputs(TileInputs& in, int64_t p, int64_t N, const float* __restrict__ enc,
+                                                 int64_t enc_stride, const float* __restrict__ views,
+                                                 int64_t views_stride, int64_t pts_per_view,
+                                                 const uint8_t* __restrict__ keep, int aligned) {
+  const bool valid = p < N;
+  const int64_t q = valid ? p : 0;
+  const float* erow = enc + q * enc_stride;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (aligned) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(erow + 16 * h) + k);
+        in.e[h][4 * k] = f.x;
+        in.e[h][4 * k + 1] = f.y;
+        in.e[h][4 * k + 2] = f.z;
+        in.e[h][4 * k + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) in.e[h][i] = __ldg(erow + 16 * h + i);
+    }
+  }
+  const float* vrow = views + (q / pts_per_view) * views_stride;
+  if ((views_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(views) & 15) == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(vrow) + k);
+      in.v[4 * k] = f.x;
+      in.v[4 * k + 1] = f.y;
+      in.v[4 * k + 2] = f.z;
+      in.v[4 * k + 3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) in.v[i] = __ldg(vrow + i);
+  }
+  in.keep = (keep != nullptr) ? __ldg(keep + q) : (uint8_t)1;
+  if (!valid) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) in.e[0][i] = in.e[1][i] = in.v[i] = 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(kTile, 2)
 mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float* __restrict__ views,
                   int64_t views_stride, int64_t pts_per_view, const float* __restrict__ weights,
@@ -123,35 +175,24 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
   uint32_t phase = 0;
 
   const int64_t n_tiles = (N + kTile - 1) / kTile;
+  TileInputs cur;
+  if ((int64_t)blockIdx.x < n_tiles)
+    load_tile_inputs(cur, (int64_t)blockIdx.x * kTile + t, N, enc, enc_stride, views, views_stride, pts_per_view, keep,
+                     aligned);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t p = tile * kTile + t;
     const bool valid = p < N;
     // ---- layer 0 input: the 32 hash features of this point
-    {
-      const float* erow = enc + (valid ? p : 0) * enc_stride;
+    put16(row, 0, cur.e[0]);
+    put16(row, 16, cur.e[1]);
+    float vsh[16];
 #pragma unroll
-      for (int c0 = 0; c0 < kIn; c0 += 16) {
-        float v[16];
-        if (aligned) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(erow + c0) + q);
-            v[4 * q] = f.x;
-            v[4 * q + 1] = f.y;
-            v[4 * q + 2] = f.z;
-            v[4 * q + 3] = f.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __ldg(erow + c0 + i);
-        }
-        if (!valid) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        }
-        put16(row, c0, v);
-      }
-    }
+    for (int i = 0; i < 16; ++i) vsh[i] = cur.v[i];
+    const uint8_t keep_cur = cur.keep;
+    // next tile's inputs: in flight while this tile runs its five layers
+    if (tile + gridDim.x < n_tiles)
+      load_tile_inputs(cur, (tile + gridDim.x) * kTile + t, N, enc, enc_stride, views, views_stride, pts_per_view, keep,
+                       aligned);
     run_layer<64, 32>(tmem, &bar, phase, s_hi + oW0 * 4, s_lo + oW0 * 4);  // h1 pre-activation
 #pragma unroll
     for (int c0 = 0; c0 < kHid; c0 += 16) {
@@ -170,10 +211,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       sigma = h2[0];
       // c = [views(16) | geo(15) | 0]
       float v[16];
-      const float* vrow = views + ((valid ? p : 0) / pts_per_view) * views_stride;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = valid ? __ldg(vrow + i) : 0.f;
-      put16(row, 0, v);
+      put16(row, 0, vsh);
 #pragma unroll
       for (int i = 0; i < 15; ++i) v[i] = h2[1 + i];
       v[15] = 0.f;
@@ -205,7 +243,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       float rgb[8];
       tmem_ld8(row + kColD, rgb);
       if (valid) {
-        const float s = (keep != nullptr && keep[p] == 0) ? 0.f : sigma;  // run_nerf_helpers.py:225
+        const float s = (keep_cur == 0) ? 0.f : sigma;  // run_nerf_helpers.py:225
         reinterpret_cast<float4*>(out)[p] = make_float4(rgb[0], rgb[1], rgb[2], s);
       }
     }
@@ -315,46 +353,46 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   uint32_t phase = 0;
 
   const int64_t n_tiles = (N + kTile - 1) / kTile;
-  for (int64_t tile = (int64_t)blockIdx.x * 2 + ctx; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
+  const int64_t tile_step = (int64_t)gridDim.x * 2;
+  TileInputs cur;
+  float4 go_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int64_t tile0 = (int64_t)blockIdx.x * 2 + ctx;
+    if (tile0 < n_tiles) {
+      const int64_t p0 = tile0 * kTile + t;
+      load_tile_inputs(cur, p0, N, enc, enc_stride, views, views_stride, pts_per_view, keep, aligned);
+      if (p0 < N) go_cur = __ldg(reinterpret_cast<const float4*>(dout) + p0);
+    }
+  }
+  for (int64_t tile = (int64_t)blockIdx.x * 2 + ctx; tile < n_tiles; tile += tile_step) {
     const int64_t p = tile * kTile + t;
     const bool valid = p < N;
     // this point's workspace column: half block t / 64, column t % 64 (a warp still writes 128 contiguous bytes)
     float* g = ws + tile * (int64_t)(kWsRowsTc * kTile) + (t >> 6) * (kWsRowsTc * kWsStride) + (t & 63);
-    // ---- inputs
-    {
-      const float* erow = enc + (valid ? p : 0) * enc_stride;
+    // ---- inputs (loaded one tile ahead)
 #pragma unroll
-      for (int c0 = 0; c0 < kIn; c0 += 16) {
-        float v[16];
-        if (aligned) {
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(erow + c0) + q);
-            v[4 * q] = f.x;
-            v[4 * q + 1] = f.y;
-            v[4 * q + 2] = f.z;
-            v[4 * q + 3] = f.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __ldg(erow + c0 + i);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (!valid) v[i] = 0.f;
-          g[(rIn + c0 + i) * kWsStride] = v[i];
-        }
-        put16(row, c0, v);
-      }
+      for (int i = 0; i < 16; ++i) g[(rIn + 16 * h + i) * kWsStride] = cur.e[h][i];
+      put16(row, 16 * h, cur.e[h]);
     }
-    float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) go = __ldg(reinterpret_cast<const float4*>(dout) + p);
-    const float dsigma = (valid && !(keep != nullptr && keep[p] == 0)) ? go.w : 0.f;
+    float vsh[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) vsh[i] = cur.v[i];
+    const float4 go = go_cur;
+    const float dsigma = (valid && cur.keep != 0) ? go.w : 0.f;
     g[(rDrgb + 0) * kWsStride] = go.x;
     g[(rDrgb + 1) * kWsStride] = go.y;
     g[(rDrgb + 2) * kWsStride] = go.z;
 #pragma unroll
     for (int i = 3; i < 8; ++i) g[(rDrgb + i) * kWsStride] = 0.f;
+    // next tile's inputs: in flight while this tile runs its nine layers
+    go_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tile + tile_step < n_tiles) {
+      const int64_t pn = (tile + tile_step) * kTile + t;
+      load_tile_inputs(cur, pn, N, enc, enc_stride, views, views_stride, pts_per_view, keep, aligned);
+      if (pn < N) go_cur = __ldg(reinterpret_cast<const float4*>(dout) + pn);
+    }
 
     // ---- forward recompute
     run_layer<64, 32>(tmem, bar_p, phase, s_hi + oW0 * 4, s_lo + oW0 * 4, sync_id, leader);
@@ -365,13 +403,9 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
       float h2[16];
       tmem_ld16(row + kColD, h2);
       float v[16];
-      const float* vrow = views + ((valid ? p : 0) / pts_per_view) * views_stride;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        v[i] = valid ? __ldg(vrow + i) : 0.f;
-        g[(rC + i) * kWsStride] = v[i];
-      }
-      put16(row, 0, v);
+      for (int i = 0; i < 16; ++i) g[(rC + i) * kWsStride] = vsh[i];
+      put16(row, 0, vsh);
 #pragma unroll
       for (int i = 0; i < 15; ++i) v[i] = h2[1 + i];
       v[15] = 0.f;
