@@ -84,7 +84,8 @@ class HashEmbedder(nn.Module):
 
     # -- storage --------------------------------------------------------------------------------
     def _level_weights(self):
-        return [emb.weight for emb in self.embeddings]
+        # plain dict lookups: nn.Module.__getattr__ on 16 children per call is measurable in the eager step
+        return [m._parameters['weight'] for m in self._modules['embeddings']._modules.values()]
 
     def _flatten_parameters(self):
         """Re-home the level tables into one contiguous buffer (keeps Parameter identity)."""

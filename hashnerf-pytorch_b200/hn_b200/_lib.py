@@ -81,7 +81,7 @@ def load() -> C.CDLL:
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and raise RuntimeError on a non-zero status."""
     global launches
-    lib = load()
+    lib = _lib if _lib is not None else load()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.hn_last_error_string().decode("utf-8", "replace")

@@ -58,19 +58,22 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-class _on:
-    """Make ``device`` current for the duration of a C call (no-op when it already is)."""
-
-    def __init__(self, device: torch.device):
-        self.guard = None if device.index in (None, torch.cuda.current_device()) else torch.cuda.device(device)
-
+class _NoGuard:
     def __enter__(self):
-        if self.guard is not None:
-            self.guard.__enter__()
+        return None
 
     def __exit__(self, *exc):
-        if self.guard is not None:
-            self.guard.__exit__(*exc)
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device: torch.device):
+    """Make ``device`` current for the duration of a C call (a shared no-op when it already is)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def _consecutive(tensors: Sequence[torch.Tensor]) -> bool:
