@@ -13,12 +13,22 @@ __device__ __forceinline__ uint32_t tv_hash(int64_t x, int64_t y, int64_t z, uin
   return hash3((uint32_t)x, (uint32_t)y, (uint32_t)z, mask);
 }
 
+// blockIdx.y = level: `cubes` == nullptr -> one level with cube size `cube`; otherwise level l uses cubes[l],
+// origin + 3*l, the table slab l and out[l] (all levels of a sweep in one launch).
 template <int F>
 __global__ void __launch_bounds__(256)
-tv_fwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ origin, int cube, int log2T,
-              float* __restrict__ out) {
+tv_fwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ origin, int cube,
+              const int32_t* __restrict__ cubes, int log2T, float* __restrict__ out) {
+  if (cubes != nullptr) {
+    const int l = blockIdx.y;
+    cube = __ldg(cubes + l);
+    origin += 3 * l;
+    table += ((size_t)l << log2T) * F;
+    out += l;
+  }
   const int n1 = cube + 1;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((int64_t)blockIdx.x * blockDim.x >= (int64_t)n1 * n1 * n1) return;  // CTA beyond this level's cube (uniform)
   const uint32_t mask = (1u << log2T) - 1u;
   float acc = 0.f;
   if (v < n1 * n1 * n1) {
@@ -69,8 +79,17 @@ tv_fwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ origi
 // d tv / d e(v) = (2 / cube) * sum over the up-to-6 grid neighbours n inside the cube of (e(v) - e(n))
 template <int F>
 __global__ void __launch_bounds__(256)
-tv_bwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ origin, int cube, int log2T,
-              const float* __restrict__ gout, float* __restrict__ dtable) {
+tv_bwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ origin, int cube,
+              const int32_t* __restrict__ cubes, int log2T, const float* __restrict__ gout,
+              float* __restrict__ dtable) {
+  if (cubes != nullptr) {
+    const int l = blockIdx.y;
+    cube = __ldg(cubes + l);
+    origin += 3 * l;
+    table += ((size_t)l << log2T) * F;
+    dtable += ((size_t)l << log2T) * F;
+    gout += l;
+  }
   const int n1 = cube + 1;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n1 * n1 * n1) return;
@@ -115,9 +134,9 @@ int hn_tv_loss_fwd(const float* table, const int64_t* origin, int cube, int log2
   const int n = (cube + 1) * (cube + 1) * (cube + 1);
   const unsigned grid = (unsigned)((n + 255) / 256);
   switch (F) {
-    case 1: hn::tv_fwd_kernel<1><<<grid, 256, 0, s>>>(table, origin, cube, log2T, out); break;
-    case 2: hn::tv_fwd_kernel<2><<<grid, 256, 0, s>>>(table, origin, cube, log2T, out); break;
-    default: hn::tv_fwd_kernel<4><<<grid, 256, 0, s>>>(table, origin, cube, log2T, out); break;
+    case 1: hn::tv_fwd_kernel<1><<<grid, 256, 0, s>>>(table, origin, cube, nullptr, log2T, out); break;
+    case 2: hn::tv_fwd_kernel<2><<<grid, 256, 0, s>>>(table, origin, cube, nullptr, log2T, out); break;
+    default: hn::tv_fwd_kernel<4><<<grid, 256, 0, s>>>(table, origin, cube, nullptr, log2T, out); break;
   }
   return hn::check_launch("tv_fwd_kernel");
 }
@@ -132,11 +151,49 @@ int hn_tv_loss_bwd(const float* table, const int64_t* origin, int cube, int log2
   const int n = (cube + 1) * (cube + 1) * (cube + 1);
   const unsigned grid = (unsigned)((n + 255) / 256);
   switch (F) {
-    case 1: hn::tv_bwd_kernel<1><<<grid, 256, 0, s>>>(table, origin, cube, log2T, gout, dtable); break;
-    case 2: hn::tv_bwd_kernel<2><<<grid, 256, 0, s>>>(table, origin, cube, log2T, gout, dtable); break;
-    default: hn::tv_bwd_kernel<4><<<grid, 256, 0, s>>>(table, origin, cube, log2T, gout, dtable); break;
+    case 1: hn::tv_bwd_kernel<1><<<grid, 256, 0, s>>>(table, origin, cube, nullptr, log2T, gout, dtable); break;
+    case 2: hn::tv_bwd_kernel<2><<<grid, 256, 0, s>>>(table, origin, cube, nullptr, log2T, gout, dtable); break;
+    default: hn::tv_bwd_kernel<4><<<grid, 256, 0, s>>>(table, origin, cube, nullptr, log2T, gout, dtable); break;
   }
   return hn::check_launch("tv_bwd_kernel");
+}
+
+int hn_tv_loss_fwd_levels(const float* tables, const int64_t* origins, const int32_t* cubes, int L, int max_cube,
+                          int log2T, int F, float* out, void* stream) {
+  HN_REQUIRE(L >= 1 && L <= HN_MAX_LEVELS, "hn_tv_loss_fwd_levels: L out of range");
+  HN_REQUIRE(max_cube >= 1 && max_cube <= 255, "hn_tv_loss_fwd_levels: cube size must be in [1,255]");
+  HN_REQUIRE(log2T >= 1 && log2T <= 30, "hn_tv_loss_fwd_levels: log2T out of range");
+  HN_REQUIRE(F == 1 || F == 2 || F == 4, "hn_tv_loss_fwd_levels: F must be 1, 2 or 4");
+  HN_REQUIRE(tables && origins && cubes && out, "hn_tv_loss_fwd_levels: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)L, s);
+  if (e != cudaSuccess) return hn::fail((int)e, "cudaMemsetAsync(tv out)");
+  const int n = (max_cube + 1) * (max_cube + 1) * (max_cube + 1);
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)L);
+  switch (F) {
+    case 1: hn::tv_fwd_kernel<1><<<grid, 256, 0, s>>>(tables, origins, 0, cubes, log2T, out); break;
+    case 2: hn::tv_fwd_kernel<2><<<grid, 256, 0, s>>>(tables, origins, 0, cubes, log2T, out); break;
+    default: hn::tv_fwd_kernel<4><<<grid, 256, 0, s>>>(tables, origins, 0, cubes, log2T, out); break;
+  }
+  return hn::check_launch("tv_fwd_kernel(levels)");
+}
+
+int hn_tv_loss_bwd_levels(const float* tables, const int64_t* origins, const int32_t* cubes, int L, int max_cube,
+                          int log2T, int F, const float* gout, float* dtables, void* stream) {
+  HN_REQUIRE(L >= 1 && L <= HN_MAX_LEVELS, "hn_tv_loss_bwd_levels: L out of range");
+  HN_REQUIRE(max_cube >= 1 && max_cube <= 255, "hn_tv_loss_bwd_levels: cube size must be in [1,255]");
+  HN_REQUIRE(log2T >= 1 && log2T <= 30, "hn_tv_loss_bwd_levels: log2T out of range");
+  HN_REQUIRE(F == 1 || F == 2 || F == 4, "hn_tv_loss_bwd_levels: F must be 1, 2 or 4");
+  HN_REQUIRE(tables && origins && cubes && gout && dtables, "hn_tv_loss_bwd_levels: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = (max_cube + 1) * (max_cube + 1) * (max_cube + 1);
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)L);
+  switch (F) {
+    case 1: hn::tv_bwd_kernel<1><<<grid, 256, 0, s>>>(tables, origins, 0, cubes, log2T, gout, dtables); break;
+    case 2: hn::tv_bwd_kernel<2><<<grid, 256, 0, s>>>(tables, origins, 0, cubes, log2T, gout, dtables); break;
+    default: hn::tv_bwd_kernel<4><<<grid, 256, 0, s>>>(tables, origins, 0, cubes, log2T, gout, dtables); break;
+  }
+  return hn::check_launch("tv_bwd_kernel(levels)");
 }
 
 }  // extern "C"

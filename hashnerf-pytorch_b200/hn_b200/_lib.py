@@ -47,6 +47,8 @@ SIGNATURES = {
     "hn_pack_rays": (_i, [_p, _l, _p, _l, _p, _l, _f, _f, _l, _p, _p]),
     "hn_tv_loss_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "hn_tv_loss_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "hn_tv_loss_fwd_levels": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "hn_tv_loss_bwd_levels": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "hn_radam_step_dev": (_i, [_p, _p, _p, _p, _l, _p, _p]),
     "hn_radam_step": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _i, _f, _p]),
 }

@@ -17,6 +17,8 @@ from typing import Callable, Optional
 
 import torch
 
+from . import ops
+
 
 class GraphedTrainStep:
     def __init__(self, n_rays: int, render_fn: Callable[[torch.Tensor], dict], loss_fn: Callable[[dict, torch.Tensor], torch.Tensor],
@@ -61,6 +63,7 @@ class GraphedTrainStep:
             self._capture()
         self.opt.graph_prepare()
         self.graph.replay()
+        ops.param_epoch[0] += 1
         return self.loss
 
     def _capture(self):

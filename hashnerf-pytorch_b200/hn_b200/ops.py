@@ -58,6 +58,11 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# bumped by every parameter update that goes through this package's raw-pointer kernels (RAdam.step, graph replay):
+# torch's own version counters do not see those writes, caches keyed on parameter values check this instead
+param_epoch = [0]
+
+
 class _NoGuard:
     def __enter__(self):
         return None
@@ -343,6 +348,43 @@ class TVLossFn(torch.autograd.Function):
             _lib.call("hn_tv_loss_bwd", w.data_ptr(), origin.data_ptr(), cube, log2T, int(w.shape[1]),
                       gout.data_ptr(), target.data_ptr(), _stream())
         return ret, None, None, None, None
+
+
+class TVSweepFn(torch.autograd.Function):
+    """tv[L] = TVSweepFn.apply(flat_tables, origins int64 [L,3], cubes int32 [L], max_cube, log2T, F, sink, *levels)
+
+    The total-variation terms of ALL levels in one launch (forward) and one launch (backward).  ``flat_tables`` is
+    the detached flat view over the level tables; ``levels`` are the level Parameters themselves (the autograd
+    inputs).  With a GradSink the backward scatters straight into the persistent gradient buffer, otherwise it
+    returns one dense gradient per level (slices of one buffer)."""
+
+    @staticmethod
+    def forward(ctx, flat_tables, origins, cubes, max_cube, log2T, F, sink, *levels):
+        dev = _need_cuda(flat_tables, origins, cubes)
+        L = len(levels)
+        out = torch.empty(L, dtype=torch.float32, device=dev)
+        with _on(dev):
+            _lib.call("hn_tv_loss_fwd_levels", flat_tables.data_ptr(), origins.data_ptr(), cubes.data_ptr(), L,
+                      int(max_cube), int(log2T), int(F), out.data_ptr(), _stream())
+        ctx.save_for_backward(flat_tables, origins, cubes)
+        ctx.meta = (L, int(max_cube), int(log2T), int(F), sink)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        flat_tables, origins, cubes = ctx.saved_tensors
+        L, max_cube, log2T, F, sink = ctx.meta
+        gout = _f32c(gout)
+        if sink is not None:
+            target = sink.acquire()
+        else:
+            target = torch.zeros(flat_tables.numel(), dtype=torch.float32, device=flat_tables.device)
+        with _on(flat_tables.device):
+            _lib.call("hn_tv_loss_bwd_levels", flat_tables.data_ptr(), origins.data_ptr(), cubes.data_ptr(), L,
+                      max_cube, log2T, F, gout.data_ptr(), target.data_ptr(), _stream())
+        if sink is not None:
+            return (None,) * (7 + L)
+        return (None,) * 7 + tuple(target.view(L, -1, F).unbind(0))
 
 
 # ----------------------------------------------------------------------------------------------

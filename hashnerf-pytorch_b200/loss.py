@@ -5,6 +5,7 @@ launches per level.
 """
 from __future__ import annotations
 
+import weakref
 from math import exp, floor, log
 
 import torch
@@ -13,11 +14,11 @@ from embedding.hash_encoding import hash  # noqa: F401  (reference import line l
 from hn_b200 import ops
 
 
-def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2_hashmap_size, n_levels=16):
-    """Squared finite differences of one level's features over a random cube of grid vertices.
+def _level_cube(min_resolution, max_resolution, level, n_levels):
+    """(grid resolution, cube size) of one level -- fp64 ``math`` arithmetic exactly as loss.py:13-22.
 
-    NOTE the resolution here is fp64 ``math`` arithmetic (loss.py:13-14) while the encoder's is fp32 tensor
-    arithmetic; they can disagree and both are kept as the reference has them."""
+    NOTE the resolution here is fp64 while the encoder's is fp32 tensor arithmetic; they can disagree (SURVEY
+    Appendix B10) and both are kept as the reference has them."""
     growth = exp((log(max_resolution) - log(min_resolution)) / (n_levels - 1))
     resolution = int(floor(min_resolution * growth ** level))
     smallest = int(min_resolution) - 1
@@ -25,16 +26,80 @@ def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2
     if smallest > largest:
         raise ValueError("ALERT! min cuboid size greater than max!")  # the reference drops into pdb here
     cube = int(floor(min(max(resolution / 10.0, smallest), largest)))
+    return resolution, cube
 
-    weight = embeddings.weight
+
+# The reference's training loop asks for the 16 levels one after the other, every step (run_nerf.py:628-635):
+# 16 random draws, 16 forward and 16 backward launches and, in Python, 16 autograd Functions -- more host time
+# than the rest of a 1024-ray step.  When the level modules belong to a HashEmbedder of this package, the first
+# request of such a sweep computes ALL levels (one draw, one launch each way, one autograd node) and the following
+# requests, as long as they ask for increasing levels of the same unchanged tables, are served from that result.
+# Set to False to evaluate every request on its own (one launch per level, the previous behaviour).
+TV_SWEEP = True
+
+
+class _Sweep:
+    __slots__ = ("key", "vec", "last", "versions")
+
+
+_SWEEPS = weakref.WeakKeyDictionary()    # HashEmbedder -> its current sweep (kept off the module: no pickling issues)
+_GEOMETRY = weakref.WeakKeyDictionary()  # HashEmbedder -> cached per-level cube sizes / spans on the device
+
+
+def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels):
+    """All levels' TV terms of ``owner`` as one [L] tensor (a fresh random cube per level, loss.py:25)."""
+    geo = _GEOMETRY.get(owner)
+    flat = owner.flat_tables()
+    dev = flat.device
+    if geo is None or geo[0] != (key[:4], dev):
+        res_cube = [_level_cube(min_resolution, max_resolution, l, n_levels) for l in range(n_levels)]
+        spans = [r - c for r, c in res_cube]
+        if min(spans) <= 0:
+            raise RuntimeError("total_variation_loss: cube does not fit the level grid (random_(0, to<=0))")
+        geo = ((key[:4], dev), spans,
+               torch.tensor([c for _, c in res_cube], dtype=torch.int32, device=dev),
+               max(c for _, c in res_cube))
+        _GEOMETRY[owner] = geo
+    _, spans, cubes, max_cube = geo
+    # the same draws, in the same order, as the reference's 16 consecutive calls make (loss.py:25): the generator
+    # stream -- and with it a seeded training run -- stays identical to the reference's
+    origins = torch.stack([torch.randint(0, sp, (3,), device=dev) for sp in spans])
+    levels = owner._level_weights()
+    sink = owner.grad_sink() if (torch.is_grad_enabled() and levels[0].requires_grad) else None
+    return ops.TVSweepFn.apply(flat, origins, cubes, max_cube, int(log2_hashmap_size), int(flat.shape[-1]), sink,
+                               *levels)
+
+
+def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2_hashmap_size, n_levels=16):
+    """Squared finite differences of one level's features over a random cube of grid vertices."""
+    weight = embeddings._parameters['weight'] if 'weight' in embeddings._parameters else embeddings.weight
+    owner = getattr(embeddings, "_hn_owner", None)
+    owner = owner() if owner is not None else None
+
+    if (TV_SWEEP and owner is not None and weight.is_cuda and getattr(embeddings, "_hn_level", None) == level
+            and owner.n_levels == n_levels and owner.log2_hashmap_size == log2_hashmap_size):
+        # a sweep is only reused for the same arguments, grad mode and tables (storage, torch version counters, and
+        # the update counter of this package's RAdam, whose kernels write through raw pointers)
+        key = (min_resolution, max_resolution, log2_hashmap_size, n_levels, torch.is_grad_enabled(),
+               owner._level_weights()[0].data_ptr(), ops.param_epoch[0])
+        sw = _SWEEPS.get(owner)
+        if (sw is None or sw.key != key or level <= sw.last
+                or sw.versions != [w._version for w in owner._level_weights()]):
+            sw = _Sweep()
+            sw.key = key
+            sw.vec = _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels)
+            sw.versions = [w._version for w in owner._level_weights()]
+            _SWEEPS[owner] = sw
+        sw.last = level
+        return sw.vec[level]
+
+    resolution, cube = _level_cube(min_resolution, max_resolution, level, n_levels)
     # loss.py:25 draws on the default device; the reference only works when that is the tables' device, so draw
     # there directly (no host round trip)
     origin = torch.randint(0, resolution - cube, (3,), device=weight.device)
     if origin.device != weight.device:
         origin = origin.to(weight.device)
     sink_info = None
-    owner = getattr(embeddings, "_hn_owner", None)
-    owner = owner() if owner is not None else None
     if owner is not None and torch.is_grad_enabled() and weight.requires_grad:
         sink = owner.grad_sink()
         if sink is not None:

@@ -156,6 +156,7 @@ class RAdam(Optimizer):
                 _lib.call("hn_radam_step", first.data_ptr(), first.grad.data_ptr(), st['exp_avg'].data_ptr(),
                           st['exp_avg_sq'].data_ptr(), n, beta1, beta2, group['eps'], group['lr'],
                           group['weight_decay'], step_size, mode, self.grad_scale, ops._stream())
+        ops.param_epoch[0] += 1  # the kernel wrote the parameters through raw pointers (no torch version bump)
         return loss
 
     # ---- CUDA-graph support ------------------------------------------------------------------------

@@ -186,6 +186,13 @@ HN_API int hn_tv_loss_fwd(const float* table, const int64_t* origin, int cube, i
                           void* stream);
 HN_API int hn_tv_loss_bwd(const float* table, const int64_t* origin, int cube, int log2T, int F, const float* gout,
                           float* dtable, void* stream);
+/* All L levels of a sweep (run_nerf.py:628-635 calls total_variation_loss once per level) in one launch:
+ * tables [L, 2^log2T, F] flat, origins int64 [L,3] and cubes int32 [L] on the device, max_cube = max(cubes)
+ * (sizes the grid), out / gout [L], dtables accumulated like hn_tv_loss_bwd, level by level. */
+HN_API int hn_tv_loss_fwd_levels(const float* tables, const int64_t* origins, const int32_t* cubes, int L,
+                                 int max_cube, int log2T, int F, float* out, void* stream);
+HN_API int hn_tv_loss_bwd_levels(const float* tables, const int64_t* origins, const int32_t* cubes, int L,
+                                 int max_cube, int log2T, int F, const float* gout, float* dtables, void* stream);
 
 /* CUDA-graph friendly form: the step-dependent scalars come from device memory,
  * hp = {beta1, beta2, eps, weight_decay*lr, step_size*lr, grad_scale, mode, unused}. */

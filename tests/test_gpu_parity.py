@@ -655,8 +655,10 @@ def test_radam_golden(golden):
     assert set(opt.state[p].keys()) == {"step", "exp_avg", "exp_avg_sq"}
 
 
-def test_tv_loss_golden(golden):
+def test_tv_loss_golden(golden, monkeypatch):
+    import loss
     from loss import total_variation_loss
+    monkeypatch.setattr(loss, "TV_SWEEP", False)  # per-level path: the cube origin comes from torch.randint
     g = golden("tv_loss")
     emb, tables = make_embedder(cases.BBOX_UNIT, 12)
     real = torch.randint
@@ -673,6 +675,59 @@ def test_tv_loss_golden(golden):
         dense = np.zeros((1 << 12, 2), np.float32)
         dense[g[f"l{level}_grad_rows"]] = g[f"l{level}_grad_vals"]
         close(emb.embeddings[level].weight.grad, dense, GRAD_RTOL, atol=1e-9)
+
+
+def test_tv_loss_sweep_matches_per_level_and_caches():
+    """All 16 levels in one launch (what the training loop's 16 consecutive calls get) == the per-level kernels on
+    the same cubes; and the sweep cache: one evaluation per increasing run of levels, a new one when the run
+    restarts, when grad mode changes or after an optimizer step."""
+    import loss
+    from hn_b200 import _lib, ops
+    from radam import RAdam
+    emb, tables = make_embedder(cases.BBOX_UNIT, 12)
+    L = 16
+    geo = [loss._level_cube(emb.base_resolution, emb.finest_resolution, l, L) for l in range(L)]
+    rs = np.random.RandomState(3)
+    origins = torch.tensor([[rs.randint(0, r - c) for _ in range(3)] for r, c in geo], dtype=torch.int64, device=DEV)
+    cubes = torch.tensor([c for _, c in geo], dtype=torch.int32, device=DEV)
+    flat = emb.flat_tables()
+    vec = ops.TVSweepFn.apply(flat, origins, cubes, max(c for _, c in geo), 12, 2, None, *emb._level_weights())
+    gout = g32(rs.rand(L).astype(np.float32))
+    (vec * gout).sum().backward()
+    got = torch.stack([e.weight.grad for e in emb.embeddings]).clone()
+    for e in emb.embeddings:
+        e.weight.grad = None
+    for l in range(L):
+        one = ops.TVLossFn.apply(emb.embeddings[l].weight, origins[l].contiguous(), geo[l][1], 12, None)
+        close(vec[l], one, 1e-6)
+        (one * gout[l]).backward()
+    want = torch.stack([e.weight.grad for e in emb.embeddings])
+    close(got, want, GRAD_RTOL, atol=1e-9)
+
+    def sweep_calls(levels, grad=True):
+        before = _lib.launches
+        with torch.set_grad_enabled(grad):
+            terms = [loss.total_variation_loss(emb.embeddings[i], emb.base_resolution, emb.finest_resolution, i, 12,
+                                               n_levels=L) for i in levels]
+        return terms, _lib.launches - before
+    terms, n = sweep_calls(range(L))
+    assert n == 1, f"16 consecutive levels must be one launch, saw {n}"
+    assert all(tm.requires_grad for tm in terms)
+    for e in emb.embeddings:
+        e.weight.grad = None
+    sum(terms).backward()
+    assert all(e.weight.grad is not None and float(e.weight.grad.abs().sum()) > 0 for e in emb.embeddings)
+    assert sweep_calls([0, 1, 2])[1] == 1 and sweep_calls([3, 4])[1] == 0      # continues the same sweep
+    assert sweep_calls([4])[1] == 1                                             # level repeated: new cubes
+    assert sweep_calls([5], grad=False)[1] == 1                                 # grad mode changed
+    assert sweep_calls([6, 7], grad=False)[1] == 0
+    opt = RAdam(list(emb.parameters()), lr=1e-3)
+    sum(sweep_calls([8])[0]).backward()
+    opt.step()
+    assert sweep_calls([9])[1] == 1, "tables changed (RAdam kernel): the sweep must be re-evaluated"
+    with torch.no_grad():
+        emb.embeddings[2].weight.mul_(1.0)                                      # torch in-place op: version bump
+    assert sweep_calls([10])[1] == 1
 
 
 def test_grad_sink_accumulation_semantics():

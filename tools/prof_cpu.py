@@ -17,5 +17,5 @@ def timed(fn, steps, warmup, dist=None):
 bench.time_loop = timed
 bench.train_step_extra(dev, 1024, steps=30, warmup=5)
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28)
-print(s.getvalue()[:6000])
+pstats.Stats(pr, stream=s).sort_stats(os.environ.get("SORT", "tottime")).print_stats(45)
+print(s.getvalue()[:9000])
