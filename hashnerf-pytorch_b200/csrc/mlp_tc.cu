@@ -194,13 +194,15 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       load_tile_inputs(cur, (tile + gridDim.x) * kTile + t, N, enc, enc_stride, views, views_stride, pts_per_view, keep,
                        aligned);
     run_layer<64, 32>(tmem, &bar, phase, s_hi + oW0 * 4, s_lo + oW0 * 4);  // h1 pre-activation
+    {
+      float v[4][16];
+      tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
 #pragma unroll
-    for (int c0 = 0; c0 < kHid; c0 += 16) {
-      float v[16];
-      tmem_ld16(row + kColD + c0, v);
+      for (int q = 0; q < 4; ++q) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      put16(row, c0, v);
+        for (int i = 0; i < 16; ++i) v[q][i] = fmaxf(v[q][i], 0.f);
+        put16(row, 16 * q, v[q]);
+      }
     }
     fence_before_sync();  // D has been read: the next MMA may overwrite it after the barrier
     run_layer<16, 64>(tmem, &bar, phase, s_hi + oW1 * 4, s_lo + oW1 * 4);  // h2 = [sigma | geo]
@@ -219,23 +221,27 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
     }
     fence_before_sync();
     run_layer<64, 32>(tmem, &bar, phase, s_hi + oW2 * 4, s_lo + oW2 * 4);  // h3
+    {
+      float v[4][16];
+      tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
 #pragma unroll
-    for (int c0 = 0; c0 < kHid; c0 += 16) {
-      float v[16];
-      tmem_ld16(row + kColD + c0, v);
+      for (int q = 0; q < 4; ++q) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      put16(row, c0, v);
+        for (int i = 0; i < 16; ++i) v[q][i] = fmaxf(v[q][i], 0.f);
+        put16(row, 16 * q, v[q]);
+      }
     }
     fence_before_sync();
     run_layer<64, 64>(tmem, &bar, phase, s_hi + oW3 * 4, s_lo + oW3 * 4);  // h4
+    {
+      float v[4][16];
+      tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
 #pragma unroll
-    for (int c0 = 0; c0 < kHid; c0 += 16) {
-      float v[16];
-      tmem_ld16(row + kColD + c0, v);
+      for (int q = 0; q < 4; ++q) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      put16(row, c0, v);
+        for (int i = 0; i < 16; ++i) v[q][i] = fmaxf(v[q][i], 0.f);
+        put16(row, 16 * q, v[q]);
+      }
     }
     fence_before_sync();
     run_layer<8, 64>(tmem, &bar, phase, s_hi + oW4 * 4, s_lo + oW4 * 4);  // rgb (N padded to 8)
@@ -292,20 +298,21 @@ __device__ __forceinline__ uint64_t epilogue64(uint32_t row, float* __restrict__
   // reads this thread's 64 accumulator columns, applies ReLU (returning the positive mask) or the gate,
   // stores to the workspace column (stride 128) and writes the next A operand
   uint64_t mask = 0;
+  float v[4][16];
+  tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    float v[16];
-    tmem_ld16(row + kColD + c0, v);
+  for (int q = 0; q < 4; ++q) {
+    const int c0 = 16 * q;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       if (RELU) {
-        if (v[i] > 0.f) mask |= (1ull << (c0 + i));
-        v[i] = fmaxf(v[i], 0.f);
+        if (v[q][i] > 0.f) mask |= (1ull << (c0 + i));
+        v[q][i] = fmaxf(v[q][i], 0.f);
       }
-      if (gated) v[i] = ((gate >> (c0 + i)) & 1ull) ? v[i] : 0.f;
-      ws_col[(c0 + i) * kWsStride] = v[i];
+      if (gated) v[q][i] = ((gate >> (c0 + i)) & 1ull) ? v[q][i] : 0.f;
+      ws_col[(c0 + i) * kWsStride] = v[q][i];
     }
-    put16(row, c0, v);
+    put16(row, c0, v[q]);
   }
   return mask;
 }
@@ -419,15 +426,16 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
     fence_before_sync();
     run_layer<64, 64>(tmem, bar_p, phase, s_hi + oW3 * 4, s_lo + oW3 * 4, sync_id, leader);
     uint64_t m4 = 0;
+    {  // h4: only its values (for dW4) and its mask are needed
+      float v[4][16];
+      tmem_ld64(row + kColD, v);
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {  // h4: only its values (for dW4) and its mask are needed
-      float v[16];
-      tmem_ld16(row + kColD + c0, v);
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (v[i] > 0.f) m4 |= (1ull << (c0 + i));
-        g[(rH4 + c0 + i) * kWsStride] = fmaxf(v[i], 0.f);
-      }
+        for (int i = 0; i < 16; ++i) {
+          if (v[q][i] > 0.f) m4 |= (1ull << (16 * q + i));
+          g[(rH4 + 16 * q + i) * kWsStride] = fmaxf(v[q][i], 0.f);
+        }
     }
     // ---- backward chain
     {
