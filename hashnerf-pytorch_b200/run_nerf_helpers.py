@@ -28,7 +28,9 @@ from models import NeRF, NeRFSmall, NeRFGradient  # noqa: F401
 
 # Misc (run_nerf_helpers.py:24-26)
 img2mse = lambda x, y: torch.mean((x - y) ** 2)
-mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.Tensor([10.]))
+# the reference's torch.Tensor([10.]) lands on the default tensor type's device (CUDA after run_nerf.py:725); built
+# on x's device here so that the helper also works without that global switch -- same value, same [1] shape
+mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], dtype=torch.float32, device=x.device))
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
