@@ -26,7 +26,18 @@ def _args(basedir, expname):
         tv_loss_weight=1e-6)
 
 
-def test_training_loop_body_checkpoint_and_render_path(tmp_path):
+@pytest.fixture(params=[False, True], ids=["default_cpu_tensors", "default_cuda_tensors"])
+def default_cuda(request):
+    """run_nerf.py:725 switches the global default tensor type to CUDA before train(); the shims must work with
+    and without that switch."""
+    if request.param:
+        torch.set_default_tensor_type('torch.cuda.FloatTensor')
+    yield request.param
+    if request.param:
+        torch.set_default_tensor_type('torch.FloatTensor')
+
+
+def test_training_loop_body_checkpoint_and_render_path(tmp_path, default_cuda):
     import run_nerf_helpers as H
     from loss import total_variation_loss
     from ray_util import get_rays
@@ -46,11 +57,12 @@ def test_training_loop_body_checkpoint_and_render_path(tmp_path):
     target_img = torch.rand(Himg, Wimg, 3, device=DEV)
     embed_fn = train_kw["embed_fn"]
     N_rand, losses = 64, []
-    for i in range(start + 1, start + 6):                      # run_nerf.py:576-651, no_batching branch
+    picks = np.random.choice(Himg * Wimg, size=[N_rand], replace=False)  # one fixed batch: the loss must go down
+    for i in range(start + 1, start + 9):                      # run_nerf.py:576-651, no_batching branch
         rays_o, rays_d = get_rays(Himg, Wimg, K, pose[:3, :4])
         coords = torch.stack(torch.meshgrid(torch.linspace(0, Himg - 1, Himg), torch.linspace(0, Wimg - 1, Wimg),
                                             indexing="ij"), -1).reshape(-1, 2)
-        sel = coords[np.random.choice(coords.shape[0], size=[N_rand], replace=False)].long()
+        sel = coords[picks].long().to(rays_o.device)
         ro, rd = rays_o[sel[:, 0], sel[:, 1]], rays_d[sel[:, 0], sel[:, 1]]
         target_s = target_img[sel[:, 0], sel[:, 1]]
         rgb, depth, acc, extras = H.render(Himg, Wimg, K, chunk=1024, rays=torch.stack([ro, rd], 0), verbose=i < 10,
@@ -74,14 +86,14 @@ def test_training_loop_body_checkpoint_and_render_path(tmp_path):
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
 
     # checkpoint with the reference's keys (run_nerf.py:663-673), reloaded by create_nerf (run_nerf_helpers.py:150-169)
-    path = os.path.join(tmp_path, expname, "{:06d}.tar".format(5))
-    torch.save({'global_step': 5,
+    path = os.path.join(tmp_path, expname, "{:06d}.tar".format(8))
+    torch.save({'global_step': 8,
                 'network_fn_state_dict': train_kw['network_fn'].state_dict(),
                 'network_fine_state_dict': train_kw['network_fine'].state_dict(),
                 'embed_fn_state_dict': train_kw['embed_fn'].state_dict(),
                 'optimizer_state_dict': optimizer.state_dict()}, path)
     train2, test2, start2, _, opt2 = H.create_nerf(args)
-    assert start2 == 5
+    assert start2 == 8
     for a, b in zip(train_kw['embed_fn'].parameters(), train2['embed_fn'].parameters()):
         assert torch.equal(a, b)
     for a, b in zip(train_kw['network_fine'].parameters(), train2['network_fine'].parameters()):
