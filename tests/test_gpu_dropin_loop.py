@@ -67,6 +67,8 @@ def test_training_loop_body_checkpoint_and_render_path(tmp_path, default_cuda):
         target_s = target_img[sel[:, 0], sel[:, 1]]
         rgb, depth, acc, extras = H.render(Himg, Wimg, K, chunk=1024, rays=torch.stack([ro, rd], 0), verbose=i < 10,
                                            retraw=True, **train_kw)
+        trans = extras['raw'][..., -1]                          # run_nerf.py:614
+        assert trans.shape == (N_rand, args.N_samples + args.N_importance)
         optimizer.zero_grad()
         loss = H.img2mse(rgb, target_s)
         psnr = H.mse2psnr(loss)
