@@ -1,0 +1,17 @@
+"""Time of the counting sort alone (and a permutation check)."""
+import json, os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "hashnerf-pytorch_b200")); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from hn_b200 import ops
+from sweep_hash import timeit
+dev = torch.device("cuda:0"); gen = torch.Generator(device=dev).manual_seed(0)
+box = torch.tensor([-1.5] * 3 + [1.5] * 3, device=dev)
+for logn in (24, 22, 20):
+    n = 1 << logn
+    x = torch.rand(n, 3, device=dev, generator=gen) * 3 - 1.5
+    g = ops.sort_grid_res(n)
+    t = timeit(lambda: ops.hash_sort_points(x, box, g), 10)
+    xs4 = ops.hash_sort_points(x, box, g)
+    rows = xs4[:, 3].contiguous().view(torch.int32).long()
+    ok = torch.equal(torch.sort(rows).values, torch.arange(n, device=dev)) and torch.equal(xs4[:, :3], x[rows])
+    print(json.dumps({"n": n, "grid": g, "sort_ms": round(t, 4), "permutation_ok": bool(ok)}), flush=True)
