@@ -36,6 +36,20 @@ def hash(coords, log2_hashmap_size):
     return ops.spatial_hash(coords, log2_hashmap_size)
 
 
+_LEVEL_OWNER = weakref.WeakKeyDictionary()  # nn.Embedding of a level -> (weakref to its HashEmbedder, level index)
+
+
+def level_owner(embedding_module):
+    """(HashEmbedder, level) the module is level ``level`` of, or (None, None)."""
+    entry = _LEVEL_OWNER.get(embedding_module)
+    if entry is None:
+        return None, None
+    owner = entry[0]()
+    if owner is None or owner.embeddings[entry[1]] is not embedding_module:
+        return None, None
+    return owner, entry[1]
+
+
 class HashEmbedder(nn.Module):
     """Reference hash_encoding.py:13-110.
 
@@ -71,9 +85,7 @@ class HashEmbedder(nn.Module):
         self._geom_cache = {}
         # let code that is handed a single level (loss.total_variation_loss gets embeddings[i]) find its way back
         # to the shared gradient buffer
-        for l, emb in enumerate(self.embeddings):
-            object.__setattr__(emb, "_hn_owner", weakref.ref(self))
-            object.__setattr__(emb, "_hn_level", l)
+        self._register_levels()
         # None: re-order large batches by grid cell before encoding (results unchanged, see ops.HashEncodeFn);
         # True / False force the choice.
         self.coherent = None
@@ -81,6 +93,21 @@ class HashEmbedder(nn.Module):
         # embeddings[l].weight.grad at its slices (see ops.GradSink); False: plain autograd gradients.
         self.fused_grad_accumulation = True
         self._sink = None
+
+    # -- level modules -> encoder ------------------------------------------------------------------
+    def _register_levels(self):
+        """Let the per-level modules find their encoder (total_variation_loss is handed a bare
+        ``embed_fn.embeddings[i]``).  Kept in a module-level weak registry, not on the modules: nothing extra is
+        pickled or deep-copied, and a copied encoder registers its own children (see __setstate__)."""
+        ref = weakref.ref(self)
+        for l, emb in enumerate(self.embeddings):
+            _LEVEL_OWNER[emb] = (ref, l)
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._sink = None          # gradient buffers belong to the object they were created for
+        self._flat_ok = False      # copied level tables are separate tensors until the next flatten
+        self._register_levels()
 
     # -- storage --------------------------------------------------------------------------------
     def _level_weights(self):

@@ -10,7 +10,7 @@ from math import exp, floor, log
 
 import torch
 
-from embedding.hash_encoding import hash  # noqa: F401  (reference import line loss.py:8)
+from embedding.hash_encoding import hash, level_owner  # noqa: F401  (hash: reference import line loss.py:8)
 from hn_b200 import ops
 
 
@@ -73,10 +73,9 @@ def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, 
 def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2_hashmap_size, n_levels=16):
     """Squared finite differences of one level's features over a random cube of grid vertices."""
     weight = embeddings._parameters['weight'] if 'weight' in embeddings._parameters else embeddings.weight
-    owner = getattr(embeddings, "_hn_owner", None)
-    owner = owner() if owner is not None else None
+    owner, own_level = level_owner(embeddings)
 
-    if (TV_SWEEP and owner is not None and weight.is_cuda and getattr(embeddings, "_hn_level", None) == level
+    if (TV_SWEEP and owner is not None and weight.is_cuda and own_level == level
             and owner.n_levels == n_levels and owner.log2_hashmap_size == log2_hashmap_size):
         # a sweep is only reused for the same arguments, grad mode and tables (storage, torch version counters, and
         # the update counter of this package's RAdam, whose kernels write through raw pointers)
@@ -103,7 +102,7 @@ def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2
     if owner is not None and torch.is_grad_enabled() and weight.requires_grad:
         sink = owner.grad_sink()
         if sink is not None:
-            sink_info = (sink, embeddings._hn_level * weight.numel())
+            sink_info = (sink, own_level * weight.numel())
     return ops.TVLossFn.apply(weight, origin, cube, log2_hashmap_size, sink_info)
 
 

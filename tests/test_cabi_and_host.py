@@ -87,6 +87,31 @@ def test_hash_embedder_host_side():
     assert emb.embeddings[2](torch.tensor([[0, 5]])).shape == (1, 2, 2)
 
 
+def test_hash_embedder_copies_and_pickles():
+    """deepcopy / pickle (EMA copies, torch.save(module)): the copy owns its level modules -- the back reference that
+    total_variation_loss uses must lead to the COPY's tables and gradient buffer, and nothing unpicklable is stored."""
+    import copy
+    import io
+    from embedding.hash_encoding import HashEmbedder, level_owner
+    emb = HashEmbedder((torch.zeros(3), torch.ones(3)), log2_hashmap_size=8)
+    assert level_owner(emb.embeddings[3]) == (emb, 3)
+    assert level_owner(torch.nn.Embedding(4, 2)) == (None, None)
+    twin = copy.deepcopy(emb)
+    assert level_owner(twin.embeddings[3]) == (twin, 3) and level_owner(emb.embeddings[3]) == (emb, 3)
+    assert twin.flat_tables().data_ptr() != emb.flat_tables().data_ptr()
+    assert torch.equal(twin.flat_tables(), emb.flat_tables())
+    buf = io.BytesIO()
+    torch.save(emb, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert level_owner(back.embeddings[15]) == (back, 15)
+    assert torch.equal(back.flat_tables(), emb.flat_tables()) and back.grad_sink() is not emb.grad_sink()
+    # a level module moved into another container no longer claims its old encoder's slot
+    stolen = emb.embeddings[2]
+    emb.embeddings[2] = torch.nn.Embedding(256, 2)
+    assert level_owner(stolen) == (None, None)
+
+
 def test_nerf_small_and_sh_host_side():
     from embedding.spherical_harmonic import SHEncoder
     from models import NeRF, NeRFSmall
