@@ -39,10 +39,19 @@ HN_API const char* hn_last_error_string(void);
 /* Multiprocessor count / compute capability of the current device (used to size persistent grids). */
 HN_API int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* Launch-shape knobs for profiling sweeps (not part of the numerical contract): keys "hash_fwd_lpg",
- * "hash_bwd_lpg" (levels per thread: 1,2,4,8,16; 0 = heuristic), "hash_bwd_agg" (warp-aggregated scatter:
- * -1 = for sorted points only, 0 = never, 1 = always), "hash_agg_max_heads", "hash_level_major", "mlp_impl"
- * (1 = tcgen05 3xTF32 tensor-core MLP, the default; 0 = FFMA fp32 MLP). */
+/* Launch-shape knobs for profiling sweeps and A/B runs (not part of the numerical contract; results stay within
+ * the stated tolerances for every setting).  Keys:
+ *   "hash_fwd_lpg", "hash_bwd_lpg"   levels per thread: 1,2,4,8,16; 0 = heuristic
+ *   "hash_bwd_agg"                   warp-aggregated scatter: -1 = sorted / ordered points only, 0 = never, 1 = always
+ *   "hash_agg_max_heads"             aggregate a level only if a warp's 32 lanes form at most this many runs (24)
+ *   "hash_level_major"               -1 = level-major grid for caller-ordered points, tile-major for sorted; 0/1 force
+ *   "hash_sort_two_level"            1 = two-level counting sort (default), 0 = single-pass sort
+ *   "hash_div_hoist"                 1 = hoisted-reciprocal cell-index division (default), 0 = per-point true division
+ *   "mlp_impl"                       1 = tcgen05 3xTF32 tensor-core MLP (default), 0 = FFMA fp32 MLP
+ *   "mlp_dw_nbuf"                    weight-gradient kernel: 1 = two CTAs/SM, one staging buffer (default); 2 = one
+ *                                    CTA/SM, two buffers
+ *   "mlp_fwd_one_cta", "mlp_dw_ablate"   profiling only (occupancy / phase ablations; the latter breaks results)
+ * Unknown keys return HN_EINVAL. */
 HN_API int hn_set_tuning(const char* key, int value);
 
 /* ---- (a3) spatial hash : embedding/hash_encoding.py:112-128 ------------------------------------ */
