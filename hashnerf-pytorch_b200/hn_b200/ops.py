@@ -204,9 +204,12 @@ SORT_MIN_POINTS = 1 << 19
 
 
 def sort_grid_res(n_points: int) -> int:
-    """About one point per cell (measured optimum at 2^24 points: 256^3 cells), capped so that the
-    counter array stays small next to the points."""
-    return int(min(256, max(16, round(n_points ** (1.0 / 3.0)))))
+    """About one point per cell, rounded to a power of two so that cell faces coincide with the voxel faces of the
+    power-of-two levels (measured, tools/exp_grid.py / exp_grid2.py: 2^24 points -> 256 is a sharp optimum of the
+    scatter, 2^22 -> 128 beats the cube root 161, 2^20 -> 128 beats 102), capped at the two-level sort's limit."""
+    import math
+    exp = round(math.log2(max(n_points, 1)) / 3.0)
+    return int(min(256, max(16, 1 << exp)))
 
 
 class GradSink:
