@@ -29,9 +29,13 @@ def bitrev16(v):
     for i in range(16):
         r |= ((v >> i) & 1) << (15 - i)
     return r
-keys["rows_bit_reversed"] = cx + G * bitrev16(row)
 keys["rows_scrambled"] = cx + G * ((row * 40503) % 65536)
-keys["rows_y_bitrev"] = cx + G * (bitrev16(cy) >> 8) + G * G * cz
+for seg in (128, 64, 32):
+    per = G // seg
+    sid = row * per + cx // seg                      # segment id, x-major inside a row
+    nseg = 65536 * per
+    keys[f"segments_{seg}_scrambled"] = (cx % seg) + seg * ((sid * 2654435761) % nseg)
+keys["rows_scrambled_mul_25173"] = cx + G * ((row * 25173) % 65536)
 for name, key in keys.items():
     order = torch.argsort(key, stable=True)
     xs4 = torch.cat([x[order], order.to(torch.int32).view(torch.float32)[:, None]], 1).contiguous()
