@@ -30,12 +30,11 @@ def bitrev16(v):
         r |= ((v >> i) & 1) << (15 - i)
     return r
 keys["rows_scrambled"] = cx + G * ((row * 40503) % 65536)
-for seg in (128, 64, 32):
-    per = G // seg
-    sid = row * per + cx // seg                      # segment id, x-major inside a row
-    nseg = 65536 * per
-    keys[f"segments_{seg}_scrambled"] = (cx % seg) + seg * ((sid * 2654435761) % nseg)
-keys["rows_scrambled_mul_25173"] = cx + G * ((row * 25173) % 65536)
+f = ((x + 1.5) / 3.0 * (2 * G)).floor().clamp(0, 2 * G - 1).long()
+octant = (f[:, 0] & 1) + 2 * (f[:, 1] & 1) + 4 * (f[:, 2] & 1)
+base = cx + G * ((row * 40503) % 65536)
+keys["rows_scrambled_then_octant"] = base * 8 + octant
+keys["rows_scrambled_then_x_half"] = base * 2 + (f[:, 0] & 1)
 for name, key in keys.items():
     order = torch.argsort(key, stable=True)
     xs4 = torch.cat([x[order], order.to(torch.int32).view(torch.float32)[:, None]], 1).contiguous()
