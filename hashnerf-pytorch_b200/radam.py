@@ -161,30 +161,50 @@ class RAdam(Optimizer):
 
     # ---- CUDA-graph support ------------------------------------------------------------------------
     # A captured graph replays kernel launches, not Python.  The step-dependent scalars therefore live in a
-    # device array refreshed by a (captured) copy from pinned host memory:
+    # device array that the captured kernels read and that is refreshed, per step, by a plain stream-ordered copy
+    # issued right before the replay:
     #     opt.graph_plan()            once, gradients present, before capture
-    #     opt.graph_launch()          inside the capture
-    #     opt.graph_prepare()         before every replay (host only: counters, lr schedule -> pinned array)
+    #     opt.graph_launch()          inside the capture (kernels only)
+    #     opt.graph_prepare()         before every replay, on the replay's stream: counters, lr schedule ->
+    #                                 one slot of a pinned ring -> async copy to the device array
+    # The ring matters: the host runs ahead of the GPU, and a single pinned row overwritten for step k+1 before the
+    # copy of step k has executed would hand step k the scalars of step k+1 (harmless-looking on one GPU, but it makes
+    # data-parallel ranks, whose hosts run ahead by different amounts, drift apart bit by bit).  A slot is rewritten
+    # only after the event recorded behind its previous copy has completed.
+    _RING = 4
+
     @torch.no_grad()
     def graph_plan(self):
         self._g_spans = self._spans()
         dev = self._g_spans[0][1][0].device
-        self._g_host = torch.zeros(len(self._g_spans), 8, dtype=torch.float32).pin_memory()
-        self._g_dev = torch.zeros(len(self._g_spans), 8, dtype=torch.float32, device=dev)
+        n = len(self._g_spans)
+        self._g_host = [torch.zeros(n, 8, dtype=torch.float32).pin_memory() for _ in range(self._RING)]
+        self._g_events = [None] * self._RING
+        self._g_slot = 0
+        self._g_dev = torch.zeros(n, 8, dtype=torch.float32, device=dev)
 
     def graph_prepare(self):
+        slot = self._g_slot
+        self._g_slot = (slot + 1) % self._RING
+        if self._g_events[slot] is not None:
+            self._g_events[slot].synchronize()       # the copy that last read this pinned slot is done
+        host = self._g_host[slot]
         for i, (group, span) in enumerate(self._g_spans):
             mode, step_size = self._advance(group, span)
             beta1, beta2 = group['betas']
-            row = self._g_host[i]
+            row = host[i]
             row[0], row[1], row[2] = beta1, beta2, group['eps']
             row[3] = group['weight_decay'] * group['lr']
             row[4] = step_size * group['lr']
             row[5], row[6] = self.grad_scale, float(mode)
+        with torch.cuda.device(self._g_dev.device):
+            self._g_dev.copy_(host, non_blocking=True)   # stream-ordered: lands before the replay's kernels
+            ev = self._g_events[slot] or torch.cuda.Event()
+            ev.record()
+            self._g_events[slot] = ev
 
     @torch.no_grad()
     def graph_launch(self):
-        self._g_dev.copy_(self._g_host, non_blocking=True)
         for i, (group, span) in enumerate(self._g_spans):
             first, st = span[0], self.state[span[0]]
             n = sum(p.numel() for p in span)
