@@ -196,7 +196,13 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, r
 
     if graphed:
         from hn_b200.graph import GraphedTrainStep
-        trainer = GraphedTrainStep(n_rand, render_fn, loss_fn, opt, dev, warmup=2)
+        grad_sync = None
+        if dist is not None:   # data parallel inside the graph: the all-reduces are captured as graph nodes
+            from hn_b200.dp import GradSync
+            sync = GradSync(list(emb.parameters()) + list(coarse.parameters()) + list(fine.parameters()))
+            opt.grad_scale = sync.grad_scale
+            grad_sync = sync.all_reduce_inline
+        trainer = GraphedTrainStep(n_rand, render_fn, loss_fn, opt, dev, warmup=2, grad_sync=grad_sync)
 
         def step():
             trainer.step(rays, target)
@@ -461,6 +467,10 @@ def run_ours(args):
         extra["train_ms_per_step_nrand8192_per_rank_dp"] = round(ms, 3)
         extra["train_step"] = ("data parallel: 8192 rays per rank, render_rays 64+128, mse+sparsity+16 TV terms, "
                                "backward, flat gradient all-reduce (GradSync), RAdam with 1/world folded in; eager")
+        if args.dp_graph:
+            rps, ms = train_step_extra(dev, 8192, steps=20, warmup=3, graphed=True, dist=dist, rank=rank, world=world)
+            extra["train_rays_per_s_nrand8192_per_rank_dp_cuda_graph"] = round(rps, 1)
+            extra["train_ms_per_step_nrand8192_per_rank_dp_cuda_graph"] = round(ms, 3)
         ms = inference_frame_extra(dev, dist=dist)
         extra["inference_800x800_ms_per_frame_rays_sharded"] = round(ms, 2)
         extra["inference_800x800_mrays_per_s_rays_sharded"] = round(0.64 / ms * 1e3, 2)
@@ -540,6 +550,9 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="1 = upload each step's points one step ahead (double buffer); >1 = split one step into "
                          "geometric pieces and overlap piece c+1's upload with piece c's compute")
+    ap.add_argument("--dp-graph", action="store_true",
+                    help="N > 1: also time the data-parallel training step as one CUDA graph with the NCCL all-reduces "
+                         "captured inside (opt-in: keeps the default run free of collective capture)")
     ap.add_argument("--bucket-overlap", action="store_true",
                     help="N > 1: all-reduce the table gradient in 4 level buckets overlapped with the scatter instead "
                          "of once after it (measured slower: splitting the scatter costs more than the overlap hides)")

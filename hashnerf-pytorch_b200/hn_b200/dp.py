@@ -112,6 +112,17 @@ class GradSync:
             w.wait()
         self._works = []
 
+    def all_reduce_inline(self) -> None:
+        """The same summed all-reduce issued on the CURRENT stream (no side stream, nothing to wait for): the form a
+        CUDA-graph capture needs (graph.GraphedTrainStep(grad_sync=...))."""
+        if self.world_size == 1:
+            return
+        flats = _flat_runs(self._grads())
+        self.bytes_last = sum(f.numel() * f.element_size() for f in flats)
+        self.calls_last = len(flats)
+        for f in flats:
+            dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group)
+
 
 class BucketedTableReducer:
     """All-reduce of the hash-table gradient in level buckets, overlapped with the scatter.

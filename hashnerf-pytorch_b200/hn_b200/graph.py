@@ -22,10 +22,15 @@ from . import ops
 
 class GraphedTrainStep:
     def __init__(self, n_rays: int, render_fn: Callable[[torch.Tensor], dict], loss_fn: Callable[[dict, torch.Tensor], torch.Tensor],
-                 optimizer, device, ray_width: int = 11, warmup: int = 3, lr_schedule: Optional[Callable[[int], float]] = None):
+                 optimizer, device, ray_width: int = 11, warmup: int = 3, lr_schedule: Optional[Callable[[int], float]] = None,
+                 grad_sync: Optional[Callable[[], None]] = None):
         """render_fn(ray_batch[n_rays, ray_width]) -> dict (e.g. a closure over render_rays);
         loss_fn(ret, target[n_rays,3]) -> scalar; optimizer: radam.RAdam.  ``warmup`` eager steps are real
-        optimisation steps (they also initialise the optimizer state and every lazy allocation)."""
+        optimisation steps (they also initialise the optimizer state and every lazy allocation).
+        ``grad_sync``: called between backward and the optimizer, eagerly and inside the capture -- data-parallel
+        runs pass ``dp.GradSync(...).all_reduce_inline`` (NCCL collectives on the capturing stream become graph
+        nodes) and set ``optimizer.grad_scale = 1 / world_size``."""
+        self._grad_sync = grad_sync
         self.opt = optimizer
         self.lr_schedule = lr_schedule
         self.global_step = 0
@@ -40,6 +45,8 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         loss = self._loss(self._render(self.rays), self.target)
         loss.backward()
+        if self._grad_sync is not None:
+            self._grad_sync()
         self.opt.step()
         return loss
 
@@ -79,5 +86,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             loss = self._loss(self._render(self.rays), self.target)
             loss.backward()
+            if self._grad_sync is not None:
+                self._grad_sync()
             self.opt.graph_launch()
             self.loss = loss.detach()

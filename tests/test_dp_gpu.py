@@ -52,6 +52,42 @@ def _loss_and_backward(emb, nets, sh, rays):
     return loss
 
 
+def _graphed_dp_check(rank, world, dev, rays, s, e):
+    """The data-parallel exchange inside a CUDA graph (opt-in, HN_TEST_DP_GRAPH=1: capturing NCCL collectives makes
+    this test take about two minutes, most of it in communicator teardown).  Passed bit-identically on 2 x B200 when
+    committed; it is the test that exposed the stale-scalar race fixed in radam.RAdam.graph_prepare."""
+    import torch.distributed as dist
+    from hn_b200 import dp
+    from radam import RAdam
+    from hn_b200.graph import GraphedTrainStep
+    from run_nerf_helpers import render_rays as _rr, run_network as _rn, img2mse
+    emb3, nets3, sh3 = _build(dev)
+    params3 = list(emb3.parameters()) + [p for n in nets3 for p in n.parameters()]
+    dp.broadcast_parameters(params3)
+    start3 = torch.cat([p.detach().reshape(-1) for p in params3]).clone()
+    opt3 = RAdam([{"params": [p for n in nets3 for p in n.parameters()], "weight_decay": 1e-6},
+                  {"params": list(emb3.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+    sync3 = dp.GradSync(params3)
+    opt3.grad_scale = sync3.grad_scale
+    q3 = lambda i, v, fn: _rn(i, v, fn, embed_fn=emb3, embeddirs_fn=sh3)
+    render_fn = lambda rb: _rr(rb, nets3[0], q3, 16, embed_fn=emb3, retraw=True, perturb=1., N_importance=16,
+                               network_fine=nets3[1], white_bkgd=True)
+    loss_fn = lambda ret, tgt: img2mse(ret["rgb_map"], tgt) + img2mse(ret["rgb0"], tgt)
+    n_local = e - s
+    trainer = GraphedTrainStep(n_local, render_fn, loss_fn, opt3, dev, warmup=2, grad_sync=sync3.all_reduce_inline)
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    for _ in range(8):
+        pick = torch.randperm(rays.shape[0], device=dev, generator=gen)[:n_local]
+        loss3 = trainer.step(rays[pick].contiguous(), torch.rand(n_local, 3, device=dev, generator=gen))
+    assert trainer.graph is not None and bool(torch.isfinite(loss3))
+    flat3 = torch.cat([p.detach().reshape(-1) for p in params3])
+    other3 = [torch.empty_like(flat3) for _ in range(world)]
+    dist.all_gather(other3, flat3)
+    same3 = all(torch.equal(o, other3[0]) for o in other3)
+    assert same3, "ranks diverged under the graphed data-parallel step"
+    assert not torch.equal(flat3, start3), "graphed steps did not train"
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
@@ -89,6 +125,8 @@ def _worker(rank, world, port, q):
         other = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(other, flat)
         assert all(torch.equal(o, other[0]) for o in other), "ranks diverged after the optimizer step"
+        if os.environ.get("HN_TEST_DP_GRAPH") == "1":
+            _graphed_dp_check(rank, world, dev, rays, s, e)
         # inference partition: rays of a frame sharded over ranks + all-gather == the frame rendered by one process
         from run_nerf_helpers import render, run_network
         H, W = 20, 24
