@@ -189,6 +189,7 @@ def test_graphed_step_matches_eager_step():
     for k in range(3):                                   # 2 eager warm-ups + the capture step (eager + replay)
         tr.step(all_rays[k], targets[k])
     opt_b, render_b, loss_b, params_b = build()
+    start = torch.cat([p.detach().reshape(-1) for p in params_b]).clone()
     seq = [0, 1, 2, 2] + list(range(3, n_steps))         # what the trainer has applied: step 2's batch twice
     for k in seq:
         opt_b.zero_grad()
@@ -198,7 +199,12 @@ def test_graphed_step_matches_eager_step():
     for k in range(3, n_steps):
         tr.step(all_rays[k], targets[k])
     torch.cuda.synchronize()
-    for pa, pb in zip(params_a, params_b):
-        scale = float(pb.detach().abs().max())
-        assert float((pa.detach() - pb.detach()).abs().max()) <= 1e-3 * scale + 1e-7, "graphed and eager runs drifted"
+    # Adam's normalisation turns the atomics' summation-order noise into visible differences on a few rarely touched
+    # table entries, so the runs are compared by the size of their difference against the size of the whole update:
+    # a step applied with the next step's scalars (the first rectified step one step early) is > 10 % of it.
+    fa = torch.cat([p.detach().reshape(-1) for p in params_a])
+    fb = torch.cat([p.detach().reshape(-1) for p in params_b])
+    update, diff = float((fb - start).norm()), float((fa - fb).norm())
+    assert update > 0 and diff <= 0.02 * update, f"graphed and eager runs drifted: |a-b| = {diff:.3e}, |update| = {update:.3e}"
+    assert float((fa - fb).abs().max()) <= 5e-3 * float(fb.abs().max())
     assert [opt_a.state[p]['step'] for p in params_a] == [opt_b.state[p]['step'] for p in params_b]
