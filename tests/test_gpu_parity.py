@@ -381,6 +381,46 @@ def test_mlp_vs_oracle(n, per_ray, mlp_impl):
         close(lin.weight.grad, w_o.grad, GRAD_RTOL, atol=2e-5 * w_o.grad.abs().max().item())
 
 
+def test_mlp_weight_kernel_variants_agree():
+    """The two launch shapes of the weight-gradient kernel (mlp_dw_nbuf: two CTAs/SM with one staging buffer, one
+    CTA/SM with two) must produce the same gradients, on a batch large enough to keep every CTA busy for a few tiles."""
+    from hn_b200 import _lib
+    sig, col = cases.mlp_weights(3)
+    rs = np.random.RandomState(12)
+    n, per_ray = 192 * 400, 192
+    enc = g32((rs.randn(n, 32) * 0.3).astype(np.float32))
+    views = g32(rs.randn(n // per_ray, 16).astype(np.float32))
+    dout = g32(rs.randn(n, 4).astype(np.float32))
+    grads = {}
+    try:
+        for nbuf in (1, 2):
+            _lib.set_tuning("mlp_dw_nbuf", nbuf)
+            net = make_mlp(sig + col)
+            (net.forward_fused(enc, views, per_ray, None) * dout).sum().backward()
+            grads[nbuf] = torch.cat([l.weight.grad.reshape(-1) for l in list(net.sigma_net) + list(net.color_net)])
+    finally:
+        _lib.set_tuning("mlp_dw_nbuf", 1)
+    assert float((grads[1] - grads[2]).abs().max()) <= GRAD_RTOL * float(grads[1].abs().max())
+
+
+def test_single_pass_sort_for_fine_grids():
+    """Grids finer than 256^3 cells use the single-pass counting sort: still a permutation that keeps the coordinates,
+    and the sorted kernels produce the plain path's results on it."""
+    from hn_b200 import ops
+    emb, tables = make_embedder(cases.BBOX_ODD, 12)
+    n = 70_001
+    x = g32(cases.points_in_box(n, cases.BBOX_ODD, seed=8))
+    box, res = emb._geometry(torch.device(DEV))
+    xs4 = ops.hash_sort_points(x, box, 300)
+    rows = xs4[:, 3].contiguous().view(torch.int32).long()
+    assert torch.equal(torch.sort(rows).values, torch.arange(n, device=DEV))
+    bit_equal(xs4[:, :3], x[rows])
+    flat = emb.flat_tables().reshape(-1)
+    want, _ = ops.hash_encode_forward(x, flat, box, res, 16, 2, 12)
+    got, _ = ops.hash_encode_forward_sorted(xs4, flat, box, res, 16, 2, 12)
+    bit_equal(got, want)
+
+
 # ---------------------------------------------------------------------------------------------- compositing
 @pytest.mark.parametrize("tag,white", [("black", False), ("white", True)])
 def test_composite_golden(golden, tag, white):
