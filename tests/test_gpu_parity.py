@@ -421,6 +421,32 @@ def test_single_pass_sort_for_fine_grids():
     bit_equal(got, want)
 
 
+def test_run_network_generic_path_matches_fused_path():
+    """run_network with callables it cannot fuse (here: NeRFSmall hidden behind a plain function, and the SH encoder
+    behind a lambda) takes the reference's expand / cat / chunked-apply / mask sequence (run_nerf_helpers.py:212-227)
+    and must agree with the fused path, including the zeroed sigma where the keep mask is False."""
+    from embedding.spherical_harmonic import SHEncoder
+    from run_nerf_helpers import run_network
+    emb, _ = make_embedder(cases.BBOX_UNIT, 12, scale=3000.0)
+    sig, col = cases.mlp_weights(9)
+    net = make_mlp(sig + col)
+    sh = SHEncoder()
+    rs = np.random.RandomState(2)
+    R, S = 37, 24
+    pts = rs.uniform(-1.6, 1.6, size=(R, S, 3)).astype(np.float32)
+    pts[0, 0] = [np.nan, 0.0, 0.0]                       # the only way a keep mask goes False at L = 16
+    dirs = rs.randn(R, 3).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+    with torch.no_grad():
+        fused = run_network(g32(pts), g32(dirs), net, embed_fn=emb, embeddirs_fn=sh)
+        generic = run_network(g32(pts), g32(dirs), lambda x: net(x), embed_fn=emb, embeddirs_fn=lambda d: sh(d),
+                              netchunk=200)
+    assert fused.shape == generic.shape == (R, S, 4)
+    assert float(generic[0, 0, 3]) == 0.0 and float(fused[0, 0, 3]) == 0.0
+    ok = torch.isfinite(fused).all(-1)
+    close(generic[ok], fused[ok], FWD_RTOL, atol=1e-6)
+
+
 # ---------------------------------------------------------------------------------------------- compositing
 @pytest.mark.parametrize("tag,white", [("black", False), ("white", True)])
 def test_composite_golden(golden, tag, white):
