@@ -421,6 +421,53 @@ def test_single_pass_sort_for_fine_grids():
     bit_equal(got, want)
 
 
+def test_mlp_plain_autograd_gradients_match_sink_gradients():
+    """NeRFSmall.fused_grad_accumulation = False returns dense gradients through autograd instead of accumulating into
+    the persistent buffer; both must give the same numbers (and accumulate over two backward passes)."""
+    sig, col = cases.mlp_weights(4)
+    rs = np.random.RandomState(5)
+    n, per_ray = 64 * 30, 64
+    enc = g32((rs.randn(n, 32) * 0.3).astype(np.float32))
+    views = g32(rs.randn(n // per_ray, 16).astype(np.float32))
+    dout = g32(rs.randn(n, 4).astype(np.float32))
+    got = {}
+    for fused in (True, False):
+        net = make_mlp(sig + col)
+        net.fused_grad_accumulation = fused
+        for _ in range(2):
+            (net.forward_fused(enc, views, per_ray, None) * dout).sum().backward()
+        got[fused] = torch.cat([l.weight.grad.reshape(-1) for l in list(net.sigma_net) + list(net.color_net)]).clone()
+    assert float((got[True] - got[False]).abs().max()) <= GRAD_RTOL * float(got[True].abs().max())
+
+
+def test_render_options_staticcam_and_render_factor():
+    """render(c2w_staticcam=...) renders the static camera's rays with the moving camera's view directions
+    (run_nerf_helpers.py:351-355); render_path(render_factor=2) renders at half resolution."""
+    from embedding.spherical_harmonic import SHEncoder
+    from run_nerf_helpers import render, render_path, run_network
+    emb, _ = make_embedder(cases.BBOX_UNIT, 12, scale=3000.0)
+    sig, col = cases.mlp_weights(6)
+    net, sh = make_mlp(sig + col), SHEncoder()
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    H, W, focal = 8, 10, 12.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    cam = g32(np.array([[1, 0, 0, 0.0], [0, 1, 0, 0.0], [0, 0, 1, 4.0]], np.float32))
+    a = np.deg2rad(25.0)                                  # a ROTATED camera: only rotations change view directions
+    moved = g32(np.array([[np.cos(a), 0, np.sin(a), 0.7], [0, 1, 0, 0.0], [-np.sin(a), 0, np.cos(a), 4.0]], np.float32))
+    kw = dict(ndc=False, near=2., far=6., use_viewdirs=True, network_fn=net, network_query_fn=qfn, N_samples=16,
+              embed_fn=emb, perturb=0., N_importance=0, white_bkgd=True)
+    with torch.no_grad():
+        plain, *_ = render(H, W, K, chunk=64, c2w=cam, **kw)
+        same_cam, *_ = render(H, W, K, chunk=64, c2w=cam, c2w_staticcam=cam, **kw)
+        static, *_ = render(H, W, K, chunk=64, c2w=moved, c2w_staticcam=cam, **kw)
+        rgbs, depths = render_path(torch.stack([torch.cat([cam, g32(np.array([[0, 0, 0, 1.0]], np.float32))])]),
+                                   (H, W, focal), K, 64, dict(kw, near=2., far=6.), render_factor=2)
+    bit_equal(same_cam, plain)
+    assert static.shape == plain.shape and bool(torch.isfinite(static).all())
+    assert not torch.equal(static, plain)          # view-dependent colour: same geometry, other directions
+    assert rgbs.shape == (1, H // 2, W // 2, 3) and depths.shape == (1, H // 2, W // 2)
+
+
 def test_run_network_generic_path_matches_fused_path():
     """run_network with callables it cannot fuse (here: NeRFSmall hidden behind a plain function, and the SH encoder
     behind a lambda) takes the reference's expand / cat / chunked-apply / mask sequence (run_nerf_helpers.py:212-227)
