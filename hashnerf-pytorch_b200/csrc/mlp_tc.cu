@@ -265,7 +265,8 @@ constexpr size_t kFwdSmemBytes = (size_t)2 * kImg * sizeof(float);  // 77,824
 // ================================================================================================
 // backward, kernel 1: recompute + dX chain, all on tcgen05, activations/deltas resident in TMEM.
 // Everything the weight gradients need is written feature-major to the workspace:
-//   per 128-point tile a [472][128] fp32 block; row r, point p at  r * 128 + p  (coalesced across the warp)
+//   per 128-point tile two [472][64] fp32 half blocks (points 0..63 | 64..127); row r, point p of a half at
+//   r * 64 + p  (a warp still stores 128 contiguous bytes; a half tile's rows of one operand are contiguous)
 // ================================================================================================
 constexpr int kWsStride = 64;  // samples per workspace row: a tile is stored as two 64-point half blocks
 constexpr int rH1 = 0, rC = 64, rH3 = 96, rH4 = 160, rDz1 = 224, rDh2 = 288, rDz3 = 304, rDz4 = 368, rIn = 432,
@@ -493,7 +494,7 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 // POINTS as the K dimension; the feature-major workspace rows are exactly K-major operands.  M = 64 feature
 // rows, N = the other tensor's features, K = 8 points per instruction.  Accumulators stay in TMEM for the
 // whole kernel (152 columns) and are flushed once with atomics.  A CTA streams 64-point half tiles:
-// load rows -> split hi/lo -> canonical image in shared memory -> 3 x 8 MMAs per matrix.
+// load rows -> split hi/lo -> 128-byte-swizzled K-major image in shared memory -> 3 x 8 MMAs per matrix.
 // ================================================================================================
 constexpr int kHalf = 64;
 constexpr uint32_t cW0 = 0, cW1 = 32, cW2 = 48, cW3 = 80, cW4 = 144;  // accumulator columns
