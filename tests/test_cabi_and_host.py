@@ -52,6 +52,29 @@ def test_ctypes_table_matches_header():
         assert n_args == len(args), f"{name}: header has {n_args} parameters, ctypes table {len(args)}"
 
 
+def test_tuning_keys_documented_in_header():
+    """Every key hn_set_tuning accepts is listed in the header's comment, and nothing else is."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "hashnerf-pytorch_b200", "csrc", "hash_encode.cu")).read()
+    accepted = set(re.findall(r'strcmp\(key, "([a-z0-9_]+)"\)', src))
+    header = open(os.path.join(root, "include", "hashnerf_b200.h")).read()
+    block = header[header.index("Launch-shape knobs"):header.index("HN_API int hn_set_tuning")]
+    documented = set(re.findall(r'"([a-z0-9_]+)"', block))
+    assert accepted and accepted == documented, (sorted(accepted - documented), sorted(documented - accepted))
+
+
+def test_sort_grid_rule_and_level_buckets():
+    from hn_b200 import ops
+    from hn_b200.dp import BucketedTableReducer
+    for n in (1, 1000, 1 << 19, 1 << 20, 1 << 22, 1 << 24, 1 << 30):
+        g = ops.sort_grid_res(n)
+        assert 16 <= g <= 256 and (g & (g - 1)) == 0
+    assert ops.sort_grid_res(1 << 24) == 256 and ops.sort_grid_res(1 << 21) == 128
+    assert BucketedTableReducer.buckets(16, 4) == [(0, 4), (4, 8), (8, 12), (12, 16)]
+    assert BucketedTableReducer.buckets(5, 2) == [(0, 2), (2, 4), (4, 5)]
+
+
 def test_hash_embedder_host_side():
     from embedding.hash_encoding import HashEmbedder, HASH_PRIMES
     import embedding.hash_encoding as he
