@@ -83,7 +83,7 @@ __device__ __forceinline__ uint64_t dense(const float* __restrict__ W, const flo
 __global__ void __launch_bounds__(kNT)
 mlp_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float* __restrict__ views,
                int64_t views_stride, int64_t pts_per_view, const float* __restrict__ weights,
-               const uint8_t* __restrict__ keep, int64_t N, float* __restrict__ out) {
+               const uint8_t* __restrict__ keep, int64_t N, float* __restrict__ out, uint32_t* __restrict__ gates) {
   extern __shared__ __align__(16) float smem[];
   float* W = smem;
   float* P = smem + kWTotal + threadIdx.x;  // ping  [64][128]
@@ -97,7 +97,7 @@ mlp_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float* _
     const float* erow = enc + p * enc_stride;
 #pragma unroll
     for (int k = 0; k < kIn; ++k) P[k * kNT] = __ldg(erow + k);
-    dense<kHid, kIn, true, false>(W + kW0, P, Q, nullptr, 0);    // h1 -> Q
+    const uint64_t m1 = dense<kHid, kIn, true, false>(W + kW0, P, Q, nullptr, 0);    // h1 -> Q
     dense<kH2, kHid, false, false>(W + kW1, Q, P, nullptr, 0);   // h2 -> P[0..15]
     const float sigma = P[0];
     const float* vrow = views + (p / pts_per_view) * views_stride;
@@ -106,8 +106,14 @@ mlp_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float* _
 #pragma unroll
     for (int k = 0; k < kGeo; ++k) Q[(kViews + k) * kNT] = P[(1 + k) * kNT];
     Q[(kCinPad - 1) * kNT] = 0.f;
-    dense<kHid, kCinPad, true, false>(W + kW2, Q, P, nullptr, 0);  // h3 -> P
-    dense<kHid, kHid, true, false>(W + kW3, P, Q, nullptr, 0);     // h4 -> Q
+    const uint64_t m3 = dense<kHid, kCinPad, true, false>(W + kW2, Q, P, nullptr, 0);  // h3 -> P
+    const uint64_t m4 = dense<kHid, kHid, true, false>(W + kW3, P, Q, nullptr, 0);     // h4 -> Q
+    if (gates != nullptr) {
+      uint2* g = reinterpret_cast<uint2*>(gates + p * 6);
+      g[0] = make_uint2((uint32_t)m1, (uint32_t)(m1 >> 32));
+      g[1] = make_uint2((uint32_t)m3, (uint32_t)(m3 >> 32));
+      g[2] = make_uint2((uint32_t)m4, (uint32_t)(m4 >> 32));
+    }
     float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll 8
     for (int k = 0; k < kHid; ++k) {
@@ -306,12 +312,18 @@ constexpr size_t kBwdSmem = (size_t)(kWBoth + 2 * kHid * kNT) * sizeof(float);  
 
 // tcgen05 implementation (mlp_tc.cu)
 int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
-               const float* weights, const uint8_t* keep, int64_t N, float* out, int aligned, cudaStream_t stream);
+               const float* weights, const uint8_t* keep, int64_t N, float* out, uint32_t* gates, int aligned,
+               cudaStream_t stream);
 int64_t mlp_tc_bwd_workspace_floats(int64_t N);
 int mlp_tc_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
                const float* weights, const uint8_t* keep, const float* dout, int64_t N, float* d_enc, float* dweights,
                float* workspace, int aligned, cudaStream_t stream);
-int g_mlp_impl = 1;  // 1 = tcgen05 3xTF32 (mlp_tc.cu, default), 0 = FFMA fp32 (this file)
+int64_t mlp_tc_bwd_fused_workspace_bytes();
+int mlp_tc_bwd_fused(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
+                     const float* weights, const uint8_t* keep, const uint32_t* gates, const float* dout, int64_t N,
+                     float* d_enc, float* dweights, float* workspace, int aligned, cudaStream_t stream);
+int g_mlp_impl = 1;      // 1 = tcgen05 tensor-core MLP (mlp_tc.cu / mlp_tc_bwd.cu, default), 0 = FFMA fp32 (this file)
+int g_mlp_bwd_impl = 1;  // with mlp_impl = 1: 1 = fused bf16x2 backward (mlp_tc_bwd.cu, default), 0 = two-kernel 3xTF32
 
 static inline bool rows16(const float* p, int64_t stride) {
   return ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && (stride % 4 == 0);
@@ -337,22 +349,25 @@ extern "C" {
 
 int64_t hn_mlp_bwd_workspace_bytes(int64_t N) {
   if (N <= 0) return 0;
+  // sized for the implementation selected now (hn_set_tuning); query again after changing it
+  if (hn::g_mlp_impl == 1 && hn::g_mlp_bwd_impl == 1) return hn::mlp_tc_bwd_fused_workspace_bytes();
   const int64_t tiles = (N + hn::kNT - 1) / hn::kNT;
   const int64_t ffma = tiles * hn::kWsRows * hn::kNT;
   const int64_t tcw = hn::mlp_tc_bwd_workspace_floats(N);
-  return (ffma > tcw ? ffma : tcw) * (int64_t)sizeof(float);  // either implementation may be selected at run time
+  return (ffma > tcw ? ffma : tcw) * (int64_t)sizeof(float);
 }
 
 int hn_mlp_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
-               const float* weights, const uint8_t* keep, int64_t N, float* out, void* stream) {
+               const float* weights, const uint8_t* keep, int64_t N, float* out, uint32_t* gates, void* stream) {
   HN_REQUIRE(N >= 0, "hn_mlp_fwd: negative N");
   HN_REQUIRE(pts_per_view >= 1, "hn_mlp_fwd: pts_per_view must be >= 1");
   HN_REQUIRE(enc_stride >= 32 && views_stride >= 0, "hn_mlp_fwd: bad row stride");
   if (N == 0) return 0;
   HN_REQUIRE(enc && views && weights && out, "hn_mlp_fwd: null pointer");
   HN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "hn_mlp_fwd: out must be 16-byte aligned");
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(gates) & 7u) == 0, "hn_mlp_fwd: gates must be 8-byte aligned");
   if (hn::g_mlp_impl == 1)
-    return hn::mlp_tc_fwd(enc, enc_stride, views, views_stride, pts_per_view, weights, keep, N, out,
+    return hn::mlp_tc_fwd(enc, enc_stride, views, views_stride, pts_per_view, weights, keep, N, out, gates,
                           hn::rows16(enc, enc_stride) ? 1 : 0, (cudaStream_t)stream);
   int rc = hn::ensure_smem_optin();
   if (rc) return rc;
@@ -360,13 +375,13 @@ int hn_mlp_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   const int64_t cap = (int64_t)hn::sm_count() * 2;  // 2 CTAs of 101 KB fit per SM
   const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
   hn::mlp_fwd_kernel<<<grid, hn::kNT, hn::kFwdSmem, (cudaStream_t)stream>>>(enc, enc_stride, views, views_stride,
-                                                                           pts_per_view, weights, keep, N, out);
+                                                                           pts_per_view, weights, keep, N, out, gates);
   return hn::check_launch("mlp_fwd_kernel");
 }
 
 int hn_mlp_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
-               const float* weights, const uint8_t* keep, const float* dout, int64_t N, float* d_enc, float* dweights,
-               float* workspace, void* stream) {
+               const float* weights, const uint8_t* keep, const uint32_t* gates, const float* dout, int64_t N,
+               float* d_enc, float* dweights, float* workspace, void* stream) {
   HN_REQUIRE(N >= 0, "hn_mlp_bwd: negative N");
   HN_REQUIRE(pts_per_view >= 1, "hn_mlp_bwd: pts_per_view must be >= 1");
   HN_REQUIRE(enc_stride >= 32 && views_stride >= 0, "hn_mlp_bwd: bad row stride");
@@ -374,6 +389,10 @@ int hn_mlp_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   HN_REQUIRE(enc && views && weights && dout && d_enc && dweights && workspace, "hn_mlp_bwd: null pointer");
   HN_REQUIRE(((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(d_enc)) & 15u) == 0,
              "hn_mlp_bwd: dout and d_enc must be 16-byte aligned");
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(gates) & 7u) == 0, "hn_mlp_bwd: gates must be 8-byte aligned");
+  if (hn::g_mlp_impl == 1 && hn::g_mlp_bwd_impl == 1)
+    return hn::mlp_tc_bwd_fused(enc, enc_stride, views, views_stride, pts_per_view, weights, keep, gates, dout, N, d_enc,
+                                dweights, workspace, hn::rows16(enc, enc_stride) ? 1 : 0, (cudaStream_t)stream);
   if (hn::g_mlp_impl == 1)
     return hn::mlp_tc_bwd(enc, enc_stride, views, views_stride, pts_per_view, weights, keep, dout, N, d_enc, dweights,
                           workspace, hn::rows16(enc, enc_stride) ? 1 : 0, (cudaStream_t)stream);

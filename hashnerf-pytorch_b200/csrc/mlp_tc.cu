@@ -12,12 +12,11 @@
 // the weights (hi and lo images, 76 KB), so two CTAs (= two tiles in flight) fit per SM; TMEM: 192 of the 256
 // columns allocated per CTA (D 64 | A_hi 64 | A_lo 64).
 #include "mlp_common.cuh"
-#include "tc05.cuh"
+#include "mlp_tc_common.cuh"
 
 namespace hn {
 namespace tc {
 
-constexpr int kTile = 128;
 // canonical K-major weight images, in floats: [N][K] each
 constexpr int oW0 = 0;                 // 64 x 32
 constexpr int oW1 = oW0 + 64 * 32;     // 16 x 64
@@ -75,14 +74,6 @@ __device__ __forceinline__ void put16(uint32_t row_taddr, int c0, const float (&
   tmem_st16(row_taddr + kColAlo + c0, lo);
 }
 
-// everything a layer boundary needs: stores visible -> the tile's 128 threads arrived -> one of them issues ->
-// all wait.  `sync_id` names the hardware barrier of this tile context (0 = the CTA-wide barrier when the CTA
-// runs a single context); `leader` is true for the context's issuing thread.
-__device__ __forceinline__ void ctx_sync(int sync_id) {
-  if (sync_id == 0) __syncthreads();
-  else asm volatile("bar.sync %0, %1;" ::"r"(sync_id), "r"(kTile) : "memory");
-}
-
 template <int N, int K>
 __device__ __forceinline__ void run_layer(uint32_t tmem, uint64_t* bar, uint32_t& phase, uint32_t w_hi, uint32_t w_lo,
                                           int sync_id = 0, bool leader = (threadIdx.x == 0)) {
@@ -99,62 +90,32 @@ __device__ __forceinline__ void run_layer(uint32_t tmem, uint64_t* bar, uint32_t
   fence_after_sync();
 }
 
-// Per-point inputs of one tile, loaded one tile ahead so that the global-load latency hides behind the layer
-// chain of the current tile: the 32 hash features, the 16 SH coefficients of the point's ray, the keep flag.
-struct TileInputs {
-  float e[2][16];
-  float v[16];
-  uint8_t keep;
-};
-
-__device__ __forceinline__ void load_tile_inputs(TileInputs& in, int64_t p, int64_t N, const float* __restrict__ enc,
-                                                 int64_t enc_stride, const float* __restrict__ views,
-                                                 int64_t views_stride, int64_t pts_per_view,
-                                                 const uint8_t* __restrict__ keep, int aligned) {
-  const bool valid = p < N;
-  const int64_t q = valid ? p : 0;
-  const float* erow = enc + q * enc_stride;
+// ReLU epilogue of a 64-wide hidden layer: D -> relu -> next A operand; GATES: also returns the mask of strictly
+// positive pre-activations (what autograd would remember; handed to the backward kernel so that its gates are
+// the forward's, whatever precision it recomputes the activations in).
+template <bool GATES>
+__device__ __forceinline__ uint64_t relu_epilogue64(uint32_t row) {
+  uint64_t mask = 0;
+  float v[4][16];
+  tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (aligned) {
+  for (int q = 0; q < 4; ++q) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(erow + 16 * h) + k);
-        in.e[h][4 * k] = f.x;
-        in.e[h][4 * k + 1] = f.y;
-        in.e[h][4 * k + 2] = f.z;
-        in.e[h][4 * k + 3] = f.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) in.e[h][i] = __ldg(erow + 16 * h + i);
+    for (int i = 0; i < 16; ++i) {
+      if (GATES && v[q][i] > 0.f) mask |= (1ull << (16 * q + i));
+      v[q][i] = fmaxf(v[q][i], 0.f);
     }
+    put16(row, 16 * q, v[q]);
   }
-  const float* vrow = views + (q / pts_per_view) * views_stride;
-  if ((views_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(views) & 15) == 0) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(vrow) + k);
-      in.v[4 * k] = f.x;
-      in.v[4 * k + 1] = f.y;
-      in.v[4 * k + 2] = f.z;
-      in.v[4 * k + 3] = f.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) in.v[i] = __ldg(vrow + i);
-  }
-  in.keep = (keep != nullptr) ? __ldg(keep + q) : (uint8_t)1;
-  if (!valid) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) in.e[0][i] = in.e[1][i] = in.v[i] = 0.f;
-  }
+  return mask;
 }
 
+template <bool GATES>
 __global__ void __launch_bounds__(kTile, 2)
 mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float* __restrict__ views,
                   int64_t views_stride, int64_t pts_per_view, const float* __restrict__ weights,
-                  const uint8_t* __restrict__ keep, int64_t N, float* __restrict__ out, int aligned) {
+                  const uint8_t* __restrict__ keep, int64_t N, float* __restrict__ out, uint32_t* __restrict__ gates,
+                  int aligned) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -194,16 +155,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       load_tile_inputs(cur, (tile + gridDim.x) * kTile + t, N, enc, enc_stride, views, views_stride, pts_per_view, keep,
                        aligned);
     run_layer<64, 32>(tmem, &bar, phase, s_hi + oW0 * 4, s_lo + oW0 * 4);  // h1 pre-activation
-    {
-      float v[4][16];
-      tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[q][i] = fmaxf(v[q][i], 0.f);
-        put16(row, 16 * q, v[q]);
-      }
-    }
+    const uint64_t m1 = relu_epilogue64<GATES>(row);
     fence_before_sync();  // D has been read: the next MMA may overwrite it after the barrier
     run_layer<16, 64>(tmem, &bar, phase, s_hi + oW1 * 4, s_lo + oW1 * 4);  // h2 = [sigma | geo]
     float sigma;
@@ -221,28 +173,10 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
     }
     fence_before_sync();
     run_layer<64, 32>(tmem, &bar, phase, s_hi + oW2 * 4, s_lo + oW2 * 4);  // h3
-    {
-      float v[4][16];
-      tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[q][i] = fmaxf(v[q][i], 0.f);
-        put16(row, 16 * q, v[q]);
-      }
-    }
+    const uint64_t m3 = relu_epilogue64<GATES>(row);
     fence_before_sync();
     run_layer<64, 64>(tmem, &bar, phase, s_hi + oW3 * 4, s_lo + oW3 * 4);  // h4
-    {
-      float v[4][16];
-      tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[q][i] = fmaxf(v[q][i], 0.f);
-        put16(row, 16 * q, v[q]);
-      }
-    }
+    const uint64_t m4 = relu_epilogue64<GATES>(row);
     fence_before_sync();
     run_layer<8, 64>(tmem, &bar, phase, s_hi + oW4 * 4, s_lo + oW4 * 4);  // rgb (N padded to 8)
     {
@@ -251,6 +185,12 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       if (valid) {
         const float s = (keep_cur == 0) ? 0.f : sigma;  // run_nerf_helpers.py:225
         reinterpret_cast<float4*>(out)[p] = make_float4(rgb[0], rgb[1], rgb[2], s);
+        if (GATES) {
+          uint2* g = reinterpret_cast<uint2*>(gates + p * 6);
+          g[0] = make_uint2((uint32_t)m1, (uint32_t)(m1 >> 32));
+          g[1] = make_uint2((uint32_t)m3, (uint32_t)(m3 >> 32));
+          g[2] = make_uint2((uint32_t)m4, (uint32_t)(m4 >> 32));
+        }
       }
     }
     fence_before_sync();
@@ -715,13 +655,16 @@ mlp_tc_bwd_weight_kernel(int64_t N, const float* __restrict__ ws, float* __restr
 int g_mlp_fwd_one_cta = 0;
 
 int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
-               const float* weights, const uint8_t* keep, int64_t N, float* out, int aligned, cudaStream_t stream) {
+               const float* weights, const uint8_t* keep, int64_t N, float* out, uint32_t* gates, int aligned,
+               cudaStream_t stream) {
   static thread_local int done_dev = -1;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail((int)e, "cudaGetDevice");
   if (done_dev != dev) {
-    e = cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    e = cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_fwd_kernel)");
+    e = cudaFuncSetAttribute(tc::mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_fwd_kernel)");
     done_dev = dev;
   }
@@ -730,8 +673,12 @@ int mlp_tc_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t
   const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
   // profiling knob (hn_set_tuning "mlp_fwd_one_cta"): pad the dynamic shared memory so that only one CTA fits per SM
   const size_t smem_bytes = g_mlp_fwd_one_cta ? (size_t)160 * 1024 : tc::kFwdSmemBytes;
-  tc::mlp_tc_fwd_kernel<<<grid, tc::kTile, smem_bytes, stream>>>(enc, enc_stride, views, views_stride,
-                                                                       pts_per_view, weights, keep, N, out, aligned);
+  if (gates != nullptr)
+    tc::mlp_tc_fwd_kernel<true><<<grid, tc::kTile, smem_bytes, stream>>>(enc, enc_stride, views, views_stride, pts_per_view,
+                                                                        weights, keep, N, out, gates, aligned);
+  else
+    tc::mlp_tc_fwd_kernel<false><<<grid, tc::kTile, smem_bytes, stream>>>(enc, enc_stride, views, views_stride, pts_per_view,
+                                                                         weights, keep, N, out, gates, aligned);
   return check_launch("mlp_tc_fwd_kernel");
 }
 

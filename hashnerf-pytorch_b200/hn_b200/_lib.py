@@ -15,6 +15,9 @@ _p = C.c_void_p
 _i = C.c_int
 _l = C.c_int64
 _f = C.c_float
+_d = C.c_double
+
+ABI_VERSION = 2  # HN_ABI_VERSION of include/hashnerf_b200.h
 
 # name -> (restype, argtypes); mirrors include/hashnerf_b200.h one to one
 SIGNATURES = {
@@ -33,9 +36,9 @@ SIGNATURES = {
     "hn_hash_encode_bwd_sorted": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
     "hn_hash_encode_bwd_sorted_levels": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p, _i, _i, _p]),
     "hn_sh_encode": (_i, [_p, _l, _i, _p, _p]),
-    "hn_mlp_fwd": (_i, [_p, _l, _p, _l, _l, _p, _p, _l, _p, _p]),
+    "hn_mlp_fwd": (_i, [_p, _l, _p, _l, _l, _p, _p, _l, _p, _p, _p]),
     "hn_mlp_bwd_workspace_bytes": (_l, [_l]),
-    "hn_mlp_bwd": (_i, [_p, _l, _p, _l, _l, _p, _p, _p, _l, _p, _p, _p, _p]),
+    "hn_mlp_bwd": (_i, [_p, _l, _p, _l, _l, _p, _p, _p, _p, _l, _p, _p, _p, _p]),
     "hn_composite_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "hn_composite_bwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hn_sample_pdf": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p]),
@@ -50,12 +53,12 @@ SIGNATURES = {
     "hn_tv_loss_fwd_levels": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "hn_tv_loss_bwd_levels": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "hn_radam_step_dev": (_i, [_p, _p, _p, _p, _l, _p, _p]),
-    "hn_radam_step": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _i, _f, _p]),
+    "hn_radam_step": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _d, _d, _d, _i, _f, _i, _p]),
 }
 
 # kernels launched per entry point (1 unless listed): hn_hash_sort_points = hist + 3 scan kernels + partition +
 # local sort (two-level form)
-KERNELS_PER_CALL = {"hn_hash_sort_points": 6, "hn_mlp_bwd": 2}
+KERNELS_PER_CALL = {"hn_hash_sort_points": 6, "hn_mlp_bwd": 2}  # hn_mlp_bwd: image prep + fused kernel
 
 _lib = None
 launches = 0  # number of CUDA kernels launched through call() (bench.py reports it as gpu_launches)
@@ -74,8 +77,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.hn_abi_version() != 1:
-        raise RuntimeError(f"libhashnerf_b200 ABI {lib.hn_abi_version()} != 1 expected by the Python shims")
+    if lib.hn_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libhashnerf_b200 ABI {lib.hn_abi_version()} != {ABI_VERSION} expected by the Python shims")
     _lib = lib
     return lib
 

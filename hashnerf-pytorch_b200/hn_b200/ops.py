@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import Optional, Sequence, Tuple
 
+import weakref
+
 import torch
 
 from . import _lib
@@ -223,15 +225,27 @@ class GradSink:
     ``set_to_none=False`` (slices zeroed in place) work, and gradients produced by other autograd paths
     (e.g. the TV loss through ``nn.Embedding``) are merged."""
 
+    _by_ptr = {}  # flat.data_ptr() -> weakref(sink): lets the optimizer report a buffer it cleared in its own pass
+
     def __init__(self, params):
         self.params = list(params)
         self.flat = None
         self._views = None  # one view of `flat` per parameter, created once (param.grad is set to these objects)
+        self.clean = False  # the whole buffer is known to be zero (cleared by a fused optimizer pass)
+
+    @classmethod
+    def note_cleared(cls, ptr: int, numel: int) -> None:
+        """Called by RAdam(fused_zero_grad=True) after a pass that zeroed ``numel`` gradients starting at ``ptr``."""
+        ref = cls._by_ptr.get(ptr)
+        sink = ref() if ref is not None else None
+        if sink is not None and sink.flat is not None and sink.flat.data_ptr() == ptr and sink.flat.numel() == numel:
+            sink.clean = True
 
     def _allocate(self):
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        GradSink._by_ptr[self.flat.data_ptr()] = weakref.ref(self)
         self._views, off = [], 0
         for p in self.params:
             self._views.append(self.flat[off:off + p.numel()].view_as(p))
@@ -244,6 +258,7 @@ class GradSink:
             self._allocate()
             fresh = True
         views = self._views
+        clean, self.clean = self.clean, False     # whatever happens next, gradients are about to be accumulated
         mine = [p.grad is v for p, v in zip(self.params, views)]
         if all(mine):
             return self.flat                      # still accumulating into our buffer (the common case)
@@ -256,7 +271,7 @@ class GradSink:
                 for v, m in zip(views, mine):
                     if not m:
                         v.zero_()
-            else:
+            elif not clean:
                 self.flat.zero_()                 # first backward since zero_grad(set_to_none=True)
         for v, g in foreign:                      # gradients that arrived through plain autograd
             v.add_(g)
@@ -431,9 +446,13 @@ class MLPFn(torch.autograd.Function):
         wflat = pack(weights)
         keep_u8 = None if keep is None else (keep if keep.dtype == torch.uint8 else keep.to(torch.uint8)).contiguous()
         out = torch.empty(N, 4, dtype=torch.float32, device=dev)
+        # what autograd would keep of the forward pass: the ReLU gates (24 bytes per point), only when a backward
+        # pass can follow
+        gates = torch.empty(N, 6, dtype=torch.int32, device=dev) if any(ctx.needs_input_grad) else None
         with _on(dev):
             _lib.call("hn_mlp_fwd", enc_r.data_ptr(), enc_stride, views_r.data_ptr(), views_stride,
-                      int(pts_per_view), wflat.data_ptr(), _ptr(keep_u8), N, out.data_ptr(), _stream())
+                      int(pts_per_view), wflat.data_ptr(), _ptr(keep_u8), N, out.data_ptr(), _ptr(gates), _stream())
+        ctx.gates = gates
         ctx.save_for_backward(enc_r, views_r, wflat, keep_u8 if keep_u8 is not None else torch.empty(0, device=dev))
         ctx.meta = (enc_stride, views_stride, int(pts_per_view), keep_u8 is not None, N,
                     ctx.needs_input_grad[0])
@@ -452,7 +471,7 @@ class MLPFn(torch.autograd.Function):
         ws = torch.empty(max(1, lib.hn_mlp_bwd_workspace_bytes(N) // 4), dtype=torch.float32, device=dev)
         with _on(dev):
             _lib.call("hn_mlp_bwd", enc_r.data_ptr(), enc_stride, views_r.data_ptr(), views_stride, ppv,
-                      wflat.data_ptr(), keep_u8.data_ptr() if has_keep else None, dout.data_ptr(), N,
+                      wflat.data_ptr(), keep_u8.data_ptr() if has_keep else None, _ptr(ctx.gates), dout.data_ptr(), N,
                       d_enc.data_ptr(), dflat.data_ptr(), ws.data_ptr(), _stream())
         if sink is not None:
             return (d_enc, None, None, None, None) + (None,) * 5

@@ -17,7 +17,8 @@ from hn_b200 import _lib, ops
 
 
 class RAdam(Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, degenerated_to_sgd=False):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, degenerated_to_sgd=False,
+                 fused_zero_grad=False):
         if not 0.0 <= lr:
             raise ValueError("Invalid learning rate: {}".format(lr))
         if not 0.0 <= eps:
@@ -28,9 +29,34 @@ class RAdam(Optimizer):
             raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
         self.degenerated_to_sgd = degenerated_to_sgd
         self.grad_scale = 1.0  # set to 1/world_size by the data-parallel wrapper after a summed all-reduce
+        # opt-in (not in the reference's signature): step() also clears the gradients it consumed, in the same
+        # pass over memory, so that the zero_grad() of the next iteration (run_nerf.py:612) has nothing left to
+        # fill.  Observable difference: p.grad reads zero right after step() instead of the consumed gradient.
+        self.fused_zero_grad = bool(fused_zero_grad)
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                         buffer=[[None, None, None] for _ in range(10)])
         super().__init__(params, defaults)
+
+    # The span plan caches parameter runs, group indices and moment pointers: anything that replaces param groups
+    # or state (checkpoint resume, unpickling, a new group) must drop it, or later lr decay would be applied to a
+    # stale group dict and the kernel would run over moments that are no longer one allocation.
+    def _drop_plan(self):
+        self.__dict__.pop("_span_cache", None)
+        self.__dict__.pop("_g_spans", None)
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._drop_plan()
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.__dict__.setdefault("grad_scale", 1.0)
+        self.__dict__.setdefault("fused_zero_grad", False)
+        self._drop_plan()
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._drop_plan()
 
     # radam.py:62-78 -- depends on the step count only
     def _rectification(self, step, beta1, beta2):
@@ -59,35 +85,35 @@ class RAdam(Optimizer):
             off += p.numel()
 
     def _spans(self):
-        """[(group, [params])]: maximal runs of parameters whose data, gradients and moments are each back to
-        back in one storage and whose step counts agree -- each run is updated by one kernel launch.  The plan is
-        cached and re-validated per step by gradient pointers (gradients normally live in persistent buffers; all
-        parameters of a cached span advance their step counts together, so the counts stay equal)."""
+        """[(group index, [params])]: maximal runs of parameters whose data, gradients and moments are each back
+        to back in one storage and whose step counts agree -- each run is updated by one kernel launch.  The plan is
+        cached and re-validated per step by the gradient pointers and the moment pointers of every parameter
+        (gradients normally live in persistent buffers; all parameters of a cached span advance their step counts
+        together, so the counts stay equal); it holds group INDICES, so a replaced group dict is picked up."""
         cached = getattr(self, "_span_cache", None)
         if cached is not None:
             sig, spans = cached
-            ok = True
-            for group in self.param_groups:
-                for p in group['params']:
-                    g = p.grad
-                    if (None if g is None else g.data_ptr()) != sig.get(id(p)):
-                        ok = False
-                        break
-                if not ok:
-                    break
-            if ok:
+            if sig == self._signature():
                 return spans
         spans = self._compute_spans()
-        sig = {}
+        self._span_cache = (self._signature(), spans)
+        return spans
+
+    def _signature(self):
+        sig = []
         for group in self.param_groups:
             for p in group['params']:
-                sig[id(p)] = None if p.grad is None else p.grad.data_ptr()
-        self._span_cache = (sig, spans)
-        return spans
+                g = p.grad
+                st = self.state.get(p)
+                m = st.get('exp_avg') if st else None
+                v = st.get('exp_avg_sq') if st else None
+                sig.append((id(p), None if g is None else g.data_ptr(), None if m is None else m.data_ptr(),
+                            None if v is None else v.data_ptr()))
+        return sig
 
     def _compute_spans(self):
         out = []
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             active = [p for p in group['params'] if p.grad is not None]
             for p in active:
                 if p.grad.is_sparse:
@@ -130,7 +156,7 @@ class RAdam(Optimizer):
                                 and ops._consecutive([sa['exp_avg_sq'], sb['exp_avg_sq']])):
                             break
                         j += 1
-                    out.append((group, run[i:j]))
+                    out.append((gi, run[i:j]))
                     i = j
         return out
 
@@ -147,15 +173,19 @@ class RAdam(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group, span in self._spans():
+        zero = 1 if self.fused_zero_grad else 0
+        for gi, span in self._spans():
+            group = self.param_groups[gi]
             mode, step_size = self._advance(group, span)
             beta1, beta2 = group['betas']
             first, st = span[0], self.state[span[0]]
             n = sum(p.numel() for p in span)
             with ops._on(first.device):
                 _lib.call("hn_radam_step", first.data_ptr(), first.grad.data_ptr(), st['exp_avg'].data_ptr(),
-                          st['exp_avg_sq'].data_ptr(), n, beta1, beta2, group['eps'], group['lr'],
-                          group['weight_decay'], step_size, mode, self.grad_scale, ops._stream())
+                          st['exp_avg_sq'].data_ptr(), n, beta1, beta2, group['eps'], float(group['lr']),
+                          float(group['weight_decay']), float(step_size), mode, self.grad_scale, zero, ops._stream())
+            if zero:
+                ops.GradSink.note_cleared(first.grad.data_ptr(), n)
         ops.param_epoch[0] += 1  # the kernel wrote the parameters through raw pointers (no torch version bump)
         return loss
 
@@ -189,7 +219,8 @@ class RAdam(Optimizer):
         if self._g_events[slot] is not None:
             self._g_events[slot].synchronize()       # the copy that last read this pinned slot is done
         host = self._g_host[slot]
-        for i, (group, span) in enumerate(self._g_spans):
+        for i, (gi, span) in enumerate(self._g_spans):
+            group = self.param_groups[gi]
             mode, step_size = self._advance(group, span)
             beta1, beta2 = group['betas']
             row = host[i]
@@ -197,6 +228,7 @@ class RAdam(Optimizer):
             row[3] = group['weight_decay'] * group['lr']
             row[4] = step_size * group['lr']
             row[5], row[6] = self.grad_scale, float(mode)
+            row[7] = 1.0 if self.fused_zero_grad else 0.0
         with torch.cuda.device(self._g_dev.device):
             self._g_dev.copy_(host, non_blocking=True)   # stream-ordered: lands before the replay's kernels
             ev = self._g_events[slot] or torch.cuda.Event()
@@ -205,7 +237,7 @@ class RAdam(Optimizer):
 
     @torch.no_grad()
     def graph_launch(self):
-        for i, (group, span) in enumerate(self._g_spans):
+        for i, (_gi, span) in enumerate(self._g_spans):
             first, st = span[0], self.state[span[0]]
             n = sum(p.numel() for p in span)
             with ops._on(first.device):

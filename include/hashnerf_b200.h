@@ -31,7 +31,7 @@ extern "C" {
 
 #define HN_EINVAL (-22)
 #define HN_MAX_LEVELS 32
-#define HN_ABI_VERSION 1
+#define HN_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------------- */
 HN_API int hn_abi_version(void);
@@ -47,7 +47,10 @@ HN_API int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   "hash_level_major"               -1 = level-major grid for caller-ordered points, tile-major for sorted; 0/1 force
  *   "hash_sort_two_level"            1 = two-level counting sort (default), 0 = single-pass sort
  *   "hash_div_hoist"                 1 = hoisted-reciprocal cell-index division (default), 0 = per-point true division
- *   "mlp_impl"                       1 = tcgen05 3xTF32 tensor-core MLP (default), 0 = FFMA fp32 MLP
+ *   "mlp_impl"                       1 = tcgen05 tensor-core MLP (default), 0 = FFMA fp32 MLP
+ *   "mlp_bwd_impl"                   tcgen05 backward: 1 = one fused kernel, bf16 hi+lo operands, weight gradients
+ *                                    formed on chip (default); 0 = two 3xTF32 kernels around an HBM workspace.
+ *                                    hn_mlp_bwd_workspace_bytes() follows the selection: query it after changing it
  *   "mlp_dw_nbuf"                    weight-gradient kernel: 1 = two CTAs/SM, one staging buffer (default); 2 = one
  *                                    CTA/SM, two buffers
  *   "mlp_fwd_one_cta", "mlp_dw_ablate"   profiling only (occupancy / phase ablations; the latter breaks results)
@@ -120,18 +123,25 @@ HN_API int hn_sh_encode(const float* dirs, int64_t N, int degree, float* out, vo
  * views + (p / pts_per_view)*views_stride (16 floats).  pts_per_view = 1 reproduces
  * NeRFSmall.forward(x[N,48]) on a split view of x; pts_per_view = S evaluates SH once per ray
  * (fuses run_nerf_helpers.py:219-222).  out: [N,4] = (rgb_raw[3], sigma).
- * keep (may be NULL): sigma is written as 0 where keep[p] == 0 (run_nerf_helpers.py:225). */
+ * keep (may be NULL): sigma is written as 0 where keep[p] == 0 (run_nerf_helpers.py:225).
+ * gates (may be NULL; [N][6] uint32, 8-byte aligned): receives, per point, the bit masks of strictly positive
+ *   pre-activations of the three ReLU layers (h1, h3, h4; 64 bits each, low word first) -- the part of the forward
+ *   state autograd would keep (models.py:157,169 F.relu).  Pass them to hn_mlp_bwd so that its ReLU derivative is
+ *   the forward's even where the backward recomputes activations in another precision. */
 #define HN_MLP_PARAMS 9344
+#define HN_MLP_GATE_WORDS 6
 HN_API int hn_mlp_fwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride,
                int64_t pts_per_view, const float* weights, const uint8_t* keep, int64_t N, float* out,
-               void* stream);
+               uint32_t* gates, void* stream);
 /* Backward: recomputes activations from (enc, views, weights).  dout [N,4].  d_enc [N,32] (dense, written),
  * dweights [9344] (ACCUMULATED).  No gradient w.r.t. views on this path (directions are data).
+ * gates (may be NULL): the masks hn_mlp_fwd wrote for the same inputs; NULL = take the sign of the recomputed
+ * pre-activations (exact for the fp32 / 3xTF32 implementations, within 1e-5 of a kink for the fused bf16x2 one).
  * workspace: caller-provided scratch of hn_mlp_bwd_workspace_bytes(N) bytes, 16-byte aligned. */
 HN_API int64_t hn_mlp_bwd_workspace_bytes(int64_t N);
 HN_API int hn_mlp_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride,
-               int64_t pts_per_view, const float* weights, const uint8_t* keep, const float* dout, int64_t N,
-               float* d_enc, float* dweights, float* workspace, void* stream);
+               int64_t pts_per_view, const float* weights, const uint8_t* keep, const uint32_t* gates,
+               const float* dout, int64_t N, float* d_enc, float* dweights, float* workspace, void* stream);
 
 /* ---- (a10) raw2outputs : run_nerf_helpers.py:577-628 ------------------------------------------- */
 /* raw [R,S,4], z [R,S], rays_d [R,3], noise [R,S] or NULL (already scaled by raw_noise_std).
@@ -171,10 +181,13 @@ HN_API int hn_ray_points(const float* rays_o, const float* rays_d, int64_t ray_s
 /* One fused pass over a flat span of n parameters: moments (:58-59), weight decay (:82-83) and the
  * rectified-Adam or degenerated-SGD update (:84-90).  step_size and the branch (`mode`: 0 = moments
  * only, 1 = adaptive, 2 = SGD-like) are computed on the host from the step count as in :62-78.
- * The gradient is multiplied by grad_scale first (1/world_size after a summed all-reduce). */
-HN_API int hn_radam_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
-                         float eps, float lr, float weight_decay, float step_size, int mode, float grad_scale,
-                         void* stream);
+ * The gradient is multiplied by grad_scale first (1/world_size after a summed all-reduce).  lr, weight_decay and
+ * step_size are doubles: the reference multiplies them as python floats before ATen rounds the product (:83,:85).
+ * zero_grad != 0 clears g in the same pass (optimizer.zero_grad(), run_nerf.py:612, folded in).  16-byte
+ * vector accesses when p, g, m and v are all 16-byte aligned, scalar otherwise. */
+HN_API int hn_radam_step(float* p, float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                         double lr, double weight_decay, double step_size, int mode, float grad_scale,
+                         int zero_grad, void* stream);
 
 /* ---- section 8f "next" row 3: ray generation / packing ------------------------------------------------- */
 /* ray_util.py:62-80: rays_d[H,W,3] for a pinhole camera (fx, fy, cx, cy) and a camera-to-world matrix c2w
@@ -204,8 +217,8 @@ HN_API int hn_tv_loss_bwd_levels(const float* tables, const int64_t* origins, co
                                  int max_cube, int log2T, int F, const float* gout, float* dtables, void* stream);
 
 /* CUDA-graph friendly form: the step-dependent scalars come from device memory,
- * hp = {beta1, beta2, eps, weight_decay*lr, step_size*lr, grad_scale, mode, unused}. */
-HN_API int hn_radam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hp, void* stream);
+ * hp = {beta1, beta2, eps, weight_decay*lr, step_size*lr, grad_scale, mode, zero_grad}. */
+HN_API int hn_radam_step_dev(float* p, float* g, float* m, float* v, int64_t n, const float* hp, void* stream);
 
 #ifdef __cplusplus
 }

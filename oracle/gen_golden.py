@@ -230,9 +230,24 @@ def gen_render_rays(ref, name, bbox, perturb, white, noise_std, R=48, S=24, Ni=4
     rays = cases.rays(R, 53)
     qfn = lambda inputs, viewdirs, fn: ref.run_network(inputs, viewdirs, fn, embed_fn=emb,
                                                        embeddirs_fn=sh, netchunk=1 << 16)
-    ret = ref.render_rays(T(rays), coarse, qfn, S, embed_fn=emb, retraw=True, perturb=perturb,
-                          N_importance=Ni, network_fine=fine, white_bkgd=white,
-                          raw_noise_std=noise_std, pytest=True)
+    # record what the reference's own sample_pdf saw and returned (run_nerf_helpers.py:548): the GPU tests feed
+    # these z_samples into the fine pass so that it can be held to the strict tolerance (the resampling itself is
+    # checked against a per-sample conditioning bound, tests/test_gpu_parity.py::sample_pdf_tolerance)
+    real_sample_pdf = ref.helpers.sample_pdf
+    spied = {}
+
+    def spy(bins, weights, N_samples, det=False, pytest=False):
+        out = real_sample_pdf(bins, weights, N_samples, det=det, pytest=pytest)
+        spied.update(bins=bins.detach().clone(), weights=weights.detach().clone(), samples=out.detach().clone())
+        return out
+
+    ref.helpers.sample_pdf = spy
+    try:
+        ret = ref.render_rays(T(rays), coarse, qfn, S, embed_fn=emb, retraw=True, perturb=perturb,
+                              N_importance=Ni, network_fine=fine, white_bkgd=white,
+                              raw_noise_std=noise_std, pytest=True)
+    finally:
+        ref.helpers.sample_pdf = real_sample_pdf
     rs = np.random.RandomState(54)
     target = rs.rand(R, 3).astype(np.float32)
     loss = ((ret["rgb_map"] - T(target)) ** 2).mean() + ((ret["rgb0"] - T(target)) ** 2).mean() \
@@ -244,6 +259,9 @@ def gen_render_rays(ref, name, bbox, perturb, white, noise_std, R=48, S=24, Ni=4
                target=target, loss=loss.detach().numpy(), grad_tables=gt)
     for k, v in ret.items():
         out["ret_" + k] = v.detach().numpy()
+    out["pdf_bins"] = spied["bins"].numpy()
+    out["pdf_weights"] = spied["weights"].numpy()
+    out["z_samples"] = spied["samples"].numpy()
     for tag, net in (("coarse", coarse), ("fine", fine)):
         for i, lin in enumerate(list(net.sigma_net) + list(net.color_net)):
             out[f"{tag}_w{i}"] = lin.weight.detach().numpy()

@@ -320,6 +320,44 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, u: torch.Tensor) -> to
     return b_lo + t * (b_hi - b_lo)                                                   # :304
 
 
+def sample_pdf_tolerance(bins: torch.Tensor, weights: torch.Tensor, u: torch.Tensor, rtol: float = 1e-5,
+                         atol: float = 2e-5, cdf_eps: float = 1e-6):
+    """Deterministic per-sample acceptance bound for an implementation of run_nerf_helpers.py:264-307 whose CDF is
+    summed in another order than ATen's sequential cumsum (ours is a warp scan).
+
+    The CDF entries of two correct fp32 implementations differ by rounding noise |d| <= ``cdf_eps`` (a 64..192-term
+    fp32 prefix sum of values <= 1: worst case ~ n * 2^-24 ~ 4e-6..1e-5, observed ~ 1e-7; 1e-6 = 16 ulp(1) is the bar
+    we hold ourselves to).  Forward error analysis of :303-304, ``t = (u - c_lo) / denom``,
+    ``sample = b_lo + t (b_hi - b_lo)``:
+      * regular samples: t moves by <= 2 cdf_eps / denom, the sample by that times the bin width;
+      * BRANCH-CHAOTIC samples: ``denom`` within 2 cdf_eps of the ``denom < 1e-5 -> 1`` switch (:302) -- which branch
+        runs is decided by rounding noise in the reference itself (CPU and CUDA ATen disagree) -- or ``u`` within
+        cdf_eps of a CDF entry (searchsorted may pick the neighbouring bin): anywhere inside the two bins involved.
+    Returns (want, tol, chaotic) with |got - want| <= tol required for EVERY sample."""
+    w = weights + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    last = cdf.shape[-1] - 1
+    below = (inds - 1).clamp(min=0)
+    above = inds.clamp(max=last)
+    c_lo, c_hi = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
+    b_lo, b_hi = torch.gather(bins, 1, below), torch.gather(bins, 1, above)
+    denom_raw = c_hi - c_lo
+    denom = torch.where(denom_raw < 1e-5, torch.ones_like(denom_raw), denom_raw)
+    want = b_lo + (u - c_lo) / denom * (b_hi - b_lo)
+    width = (b_hi - b_lo).abs()
+    # widths of the neighbouring bins, for samples that may land next door
+    w_prev = (b_lo - torch.gather(bins, 1, (below - 1).clamp(min=0))).abs()
+    w_next = (torch.gather(bins, 1, (above + 1).clamp(max=last)) - b_hi).abs()
+    chaotic = ((denom_raw - 1e-5).abs() <= 2 * cdf_eps) | ((u - c_lo).abs() <= cdf_eps) | ((c_hi - u).abs() <= cdf_eps)
+    regular = width * torch.clamp(2 * cdf_eps / denom, max=1.0)
+    tol = rtol * want.abs() + atol + torch.where(chaotic, width + torch.maximum(w_prev, w_next), regular)
+    return want, tol, chaotic
+
+
 def det_u(n_rays: int, n_importance: int) -> torch.Tensor:
     """run_nerf_helpers.py:271-272."""
     return torch.linspace(0.0, 1.0, steps=n_importance).expand(n_rays, n_importance)
@@ -344,10 +382,14 @@ def coarse_z(near: torch.Tensor, far: torch.Tensor, n_samples: int, lindisp: boo
 
 def render_rays(ray_batch: torch.Tensor, enc, coarse_w, fine_w, n_samples: int, n_importance: int,
                 t_rand=None, u=None, noise0=None, noise1=None, lindisp=False, white_bkgd=False,
-                perturb: float = 0.0, sh_degree: int = 4):
+                perturb: float = 0.0, sh_degree: int = 4, z_samples=None):
     """run_nerf_helpers.py:464-574 with every random draw passed in explicitly.
 
-    ``ray_batch`` [R, 11] = (o, d, near, far, viewdir).  Returns the reference's output dict."""
+    ``ray_batch`` [R, 11] = (o, d, near, far, viewdir).  Returns the reference's output dict plus the inputs and
+    the output of the resampling step (``pdf_bins``, ``pdf_weights``, ``pdf_u``, ``z_samples``).
+    ``z_samples`` [R, Ni], if given, replaces the output of sample_pdf (:548): a checker can hand in the depths
+    the implementation under test drew -- after holding them to ``sample_pdf_tolerance`` -- so that everything
+    downstream is compared on identical sample positions with the strict tolerance."""
     R = ray_batch.shape[0]
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None                 # :510
@@ -363,6 +405,10 @@ def render_rays(ray_batch: torch.Tensor, enc, coarse_w, fine_w, n_samples: int, 
         if u is None:
             u = det_u(R, n_importance)
         z_new = sample_pdf(mids, wts[:, 1:-1], u).detach()                            # :548-549
+        ret.update(pdf_bins=mids.detach(), pdf_weights=wts[:, 1:-1].detach(), pdf_u=u, z_samples_own=z_new)
+        if z_samples is not None:
+            z_new = z_samples.detach()
+        ret.update(z_samples=z_new)
         z, _ = torch.sort(torch.cat([z, z_new], -1), -1)                              # :551
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]                 # :552
         raw = run_network(pts, viewdirs, fine_w if fine_w is not None else coarse_w, enc, sh_degree)

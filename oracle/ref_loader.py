@@ -7,8 +7,9 @@ build container, where ``/root/reference`` exists) to produce the fixtures under
 when the reference tree happens to be present.  The GPU box has no ``/root/reference``: every
 caller must check :func:`available` first.
 
-No reference source is copied into this repository: the files are read where they lie and
-exec'd with the import-time patches listed in SURVEY.md section 8c:
+No reference source is copied into this repository's history: the files are read where they lie
+(``/root/reference``, or the git-ignored copy ``oracle/_ref/`` that ``oracle/make_ref.py`` makes so that the same
+loader works on the GPU box) and exec'd with the import-time patches listed in SURVEY.md section 8c:
 
 * ``embedding/hash_encoding.py:10-11`` allocates ``BOX_OFFSETS`` with ``device='cuda'``;
   the string is replaced by the requested device so the module imports without a driver.
@@ -23,7 +24,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("HASHNERF_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # made by oracle/make_ref.py
+
+
+def _find_root() -> str:
+    """The live checkout if there is one (build container), else the git-ignored copy that travels to the GPU box."""
+    env = os.environ.get("HASHNERF_REFERENCE_ROOT")
+    for cand in (env, "/root/reference", _VENDORED):
+        if cand and os.path.isfile(os.path.join(cand, "embedding", "hash_encoding.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

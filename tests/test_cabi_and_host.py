@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in _declared():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert lib.hn_abi_version() == 1
+    assert lib.hn_abi_version() == 2
     # argument validation happens before any CUDA call, so it is testable without a GPU
     lib.hn_last_error_string.restype = ctypes.c_char_p
     rc = lib.hn_sh_encode(None, ctypes.c_int64(4), 9, None, None)

@@ -82,14 +82,15 @@ def test_mlp_guard_bands(n, ppv, impl):
         views = torch.randn((n + ppv - 1) // ppv, 16, device=DEV)
         w = torch.randn(9344, device=DEV) * 0.1
         dout = torch.randn(n, 4, device=DEV)
-        out, d_enc, dw = Guarded(n * 16), Guarded(n * 32 * 4), Guarded(9344 * 4)
+        out, d_enc, dw, gates = Guarded(n * 16), Guarded(n * 32 * 4), Guarded(9344 * 4), Guarded(n * 24)
         ws = Guarded(lib.hn_mlp_bwd_workspace_bytes(n))
         dw.view(torch.float32, (9344,)).zero_()
-        _lib.call("hn_mlp_fwd", enc.data_ptr(), 32, views.data_ptr(), 16, ppv, w.data_ptr(), None, n, out.ptr, s)
-        _lib.call("hn_mlp_bwd", enc.data_ptr(), 32, views.data_ptr(), 16, ppv, w.data_ptr(), None, dout.data_ptr(), n,
-                  d_enc.ptr, dw.ptr, ws.ptr, s)
+        _lib.call("hn_mlp_fwd", enc.data_ptr(), 32, views.data_ptr(), 16, ppv, w.data_ptr(), None, n, out.ptr,
+                  gates.ptr, s)
+        _lib.call("hn_mlp_bwd", enc.data_ptr(), 32, views.data_ptr(), 16, ppv, w.data_ptr(), None, gates.ptr,
+                  dout.data_ptr(), n, d_enc.ptr, dw.ptr, ws.ptr, s)
         torch.cuda.synchronize()
-        for g, what in ((out, "mlp out"), (d_enc, "d_enc"), (dw, "dweights"), (ws, "mlp workspace")):
+        for g, what in ((out, "mlp out"), (d_enc, "d_enc"), (dw, "dweights"), (ws, "mlp workspace"), (gates, "gates")):
             g.check(f"{what} (impl {impl})")
         assert bool(torch.isfinite(out.view(torch.float32, (n, 4))).all())
     finally:
