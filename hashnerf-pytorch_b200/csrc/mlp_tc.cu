@@ -76,14 +76,17 @@ __device__ __forceinline__ void put16(uint32_t row_taddr, int c0, const float (&
 
 template <int N, int K>
 __device__ __forceinline__ void run_layer(uint32_t tmem, uint64_t* bar, uint32_t& phase, uint32_t w_hi, uint32_t w_lo,
-                                          int sync_id = 0, bool leader = (threadIdx.x == 0)) {
+                                          int sync_id, bool leader_warp) {
   wait_st();
   fence_before_sync();
   ctx_sync(sync_id);
-  if (leader) {
-    fence_after_sync();
-    issue_layer<N, K>(tmem, w_hi, w_lo);
-    umma_commit(bar);
+  if (leader_warp) {  // warp-uniform branch, one elected lane issues: descriptors stay in uniform registers
+    if (elect_one()) {
+      fence_after_sync();
+      issue_layer<N, K>(tmem, w_hi, w_lo);
+      umma_commit(bar);
+    }
+    __syncwarp();
   }
   mbar_wait(bar, phase);
   phase ^= 1u;
@@ -100,11 +103,14 @@ __device__ __forceinline__ uint64_t relu_epilogue64(uint32_t row) {
   tmem_ld64(row + kColD, v);  // all four loads in flight, one wait
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
+    if (GATES) {  // four independent 4-bit chains per quarter instead of one 64-long chain of predicated ORs
+      uint32_t part[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (GATES && v[q][i] > 0.f) mask |= (1ull << (16 * q + i));
-      v[q][i] = fmaxf(v[q][i], 0.f);
+      for (int i = 0; i < 16; ++i) part[i >> 2] |= (v[q][i] > 0.f) ? (1u << i) : 0u;
+      mask |= (uint64_t)((part[0] | part[1]) | (part[2] | part[3])) << (16 * q);
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[q][i] = fmaxf(v[q][i], 0.f);
     put16(row, 16 * q, v[q]);
   }
   return mask;
@@ -119,7 +125,9 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
-  const int t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);  // warp-uniform for the compiler too
+  const bool leader_warp = (warp == 0);
   stage_weights(weights, smem);
   if (t == 0) {
     mbar_init(&bar, 1);
@@ -130,7 +138,7 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
   const uint32_t row = tmem + ((uint32_t)(warp * 32) << 16);  // this thread's lane, column 0
   const uint32_t s_hi = smem_u32(smem), s_lo = smem_u32(smem + kImg);
   uint32_t phase = 0;
@@ -154,10 +162,10 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
     if (tile + gridDim.x < n_tiles)
       load_tile_inputs(cur, (tile + gridDim.x) * kTile + t, N, enc, enc_stride, views, views_stride, pts_per_view, keep,
                        aligned);
-    run_layer<64, 32>(tmem, &bar, phase, s_hi + oW0 * 4, s_lo + oW0 * 4);  // h1 pre-activation
+    run_layer<64, 32>(tmem, &bar, phase, s_hi + oW0 * 4, s_lo + oW0 * 4, 0, leader_warp);  // h1 pre-activation
     const uint64_t m1 = relu_epilogue64<GATES>(row);
     fence_before_sync();  // D has been read: the next MMA may overwrite it after the barrier
-    run_layer<16, 64>(tmem, &bar, phase, s_hi + oW1 * 4, s_lo + oW1 * 4);  // h2 = [sigma | geo]
+    run_layer<16, 64>(tmem, &bar, phase, s_hi + oW1 * 4, s_lo + oW1 * 4, 0, leader_warp);  // h2 = [sigma | geo]
     float sigma;
     {
       float h2[16];
@@ -172,13 +180,13 @@ mlp_tc_fwd_kernel(const float* __restrict__ enc, int64_t enc_stride, const float
       put16(row, 16, v);
     }
     fence_before_sync();
-    run_layer<64, 32>(tmem, &bar, phase, s_hi + oW2 * 4, s_lo + oW2 * 4);  // h3
+    run_layer<64, 32>(tmem, &bar, phase, s_hi + oW2 * 4, s_lo + oW2 * 4, 0, leader_warp);  // h3
     const uint64_t m3 = relu_epilogue64<GATES>(row);
     fence_before_sync();
-    run_layer<64, 64>(tmem, &bar, phase, s_hi + oW3 * 4, s_lo + oW3 * 4);  // h4
+    run_layer<64, 64>(tmem, &bar, phase, s_hi + oW3 * 4, s_lo + oW3 * 4, 0, leader_warp);  // h4
     const uint64_t m4 = relu_epilogue64<GATES>(row);
     fence_before_sync();
-    run_layer<8, 64>(tmem, &bar, phase, s_hi + oW4 * 4, s_lo + oW4 * 4);  // rgb (N padded to 8)
+    run_layer<8, 64>(tmem, &bar, phase, s_hi + oW4 * 4, s_lo + oW4 * 4, 0, leader_warp);  // rgb (N padded to 8)
     {
       float rgb[8];
       tmem_ld8(row + kColD, rgb);
@@ -270,7 +278,7 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   __shared__ uint32_t tmem_slot;
   const int ctx = threadIdx.x / kTile, t = threadIdx.x % kTile, warp = t >> 5;
   const int sync_id = 1 + ctx;
-  const bool leader = (t == 0);
+  const bool leader = (warp == 0);  // warp-level: run_layer elects one lane
   uint64_t* bar_p = &bars[ctx];
   {
     float* hi = smem;

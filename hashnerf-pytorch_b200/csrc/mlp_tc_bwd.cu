@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_prep_kernel(const float* __restri
 // ---- TMEM / shared-memory plan -------------------------------------------------------------------------------
 constexpr uint32_t fColD = 0, fColAhi = 64, fColAlo = 96, fCtxCols = 128;
 constexpr uint32_t fAccBase = 256, fAccCols = 80;
+constexpr uint32_t fStashBase = 416, fStashCols = 32;  // per context: the hi words of h1, parked until dW1 needs them
 constexpr uint32_t kLane16 = 16u << 16;  // TMEM address of the second M = 64 accumulator of a column range
 constexpr uint32_t aW3 = 0, aW0 = 0 + kLane16, aW2 = 32 + kLane16, aW1 = 64, aW4 = 64 + kLane16;
 constexpr uint32_t kLineBuf = kTile * 128;            // one [point][64 x bf16] line buffer: 16 KB
@@ -141,19 +142,35 @@ enum : int { kToA = 1, kToX = 2, kToY = 4 };
 
 struct Ctx {
   uint32_t tmem, row;          // this context's TMEM base; + this thread's lane
+  uint32_t stash;              // this thread's lane of the context's stash columns
   uint8_t *xh, *xl, *yh, *yl;  // this thread's lines in the X / Y buffers
   int sw;
+  uint64_t* bar_dw;            // completes when the weight-gradient MMAs issued last have read X / Y / Z
+  uint32_t phase_dw;
+  bool dw_pending;
 };
+
+// X, Y and Z may be overwritten only after the dW MMAs that read them are done.  They are issued BEHIND the layer
+// MMAs of the same step and committed to their own barrier, so they execute while this context's threads already
+// fetch the layer's accumulator from TMEM.
+__device__ __forceinline__ void wait_dw(Ctx& c) {
+  if (c.dw_pending) {
+    mbar_wait(c.bar_dw, c.phase_dw);
+    c.phase_dw ^= 1u;
+    c.dw_pending = false;
+  }
+}
 
 // reads this thread's 64 accumulator columns, applies ReLU (RELU: returns the positive mask; with `have_gate` the
 // forward pass's mask decides instead of the recomputed sign) or the gate mask, packs to bf16 pairs and writes the
 // words to the next A operand and / or this thread's X / Y line.  KEEP: also returns the words (the h1 stash).
-template <bool RELU, int DEST, bool KEEP>
-__device__ __forceinline__ uint64_t epilogue64(const Ctx& c, uint64_t gate, uint32_t (&keep_hi)[32], uint32_t (&keep_lo)[32],
-                                               bool have_gate = false) {
+template <bool RELU, bool GATES, int DEST, bool KEEP>
+__device__ __forceinline__ uint64_t epilogue64(Ctx& c, uint64_t gate, uint32_t (&keep_hi)[32], uint32_t (&keep_lo)[32]) {
+  constexpr bool have_gate = GATES;
   uint64_t mask = 0;
   float v[4][16];
   tmem_ld64(c.row + fColD, v);
+  if (DEST & (kToX | kToY)) wait_dw(c);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -173,12 +190,10 @@ __device__ __forceinline__ uint64_t epilogue64(const Ctx& c, uint64_t gate, uint
     }
     if (DEST & kToX) put_chunks(c.xh, c.xl, c.sw, 2 * q, hi, lo);
     if (DEST & kToY) put_chunks(c.yh, c.yl, c.sw, 2 * q, hi, lo);
-    if (KEEP) {
+    if (KEEP) {  // the h1 stash: hi words parked in spare TMEM columns, lo words kept in registers
+      tmem_st8(c.stash + 8 * q, hi);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        keep_hi[8 * q + i] = hi[i];
-        keep_lo[8 * q + i] = lo[i];
-      }
+      for (int i = 0; i < 8; ++i) keep_lo[8 * q + i] = lo[i];
     }
   }
   return (RELU && !have_gate) ? mask : gate;
@@ -227,6 +242,7 @@ __device__ __forceinline__ void step(int sync_id, bool leader_warp, uint64_t* ba
   fence_after_sync();
 }
 
+template <bool HAVE_GATES>
 __global__ void __launch_bounds__(2 * kTile, 1)
 mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const float* __restrict__ views,
                         int64_t views_stride, int64_t pts_per_view, const uint16_t* __restrict__ images,
@@ -235,7 +251,7 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
                         float* __restrict__ dweights, int aligned) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t bars[3];  // [0], [1]: the contexts' MMA barriers; [2]: weight images landed
+  __shared__ __align__(8) uint64_t bars[5];  // [0], [1]: layer MMAs of context 0 / 1; [2], [3]: their dW MMAs; [4]: images
   __shared__ uint32_t tmem_slot;
   // warp-uniform ids, broadcast from lane 0 so that the compiler keeps everything derived from them (TMEM and
   // shared-memory operand addresses, descriptors) in uniform registers: the MMA issue sequence is then a handful
@@ -247,13 +263,12 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   uint64_t* bar = &bars[ctx];
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
     // the nine weight images (hi + lo), prepared once per launch by mlp_bwd_prep_kernel: one TMA bulk copy
-    mbar_arrive_expect_tx(&bars[2], kImgBytes);
-    bulk_g2s(smem, images, kImgBytes, &bars[2]);
+    mbar_arrive_expect_tx(&bars[4], kImgBytes);
+    bulk_g2s(smem, images, kImgBytes, &bars[4]);
   }
   if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
   fence_before_sync();
@@ -266,12 +281,16 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   Ctx c;
   c.tmem = tmem_base + (uint32_t)ctx * fCtxCols;
   c.row = c.tmem + ((uint32_t)(warp * 32) << 16);
+  c.stash = tmem_base + fStashBase + (uint32_t)ctx * fStashCols + ((uint32_t)(warp * 32) << 16);
   uint8_t* cbase = smem + kImgBytes + (uint32_t)ctx * kCtxBytes;
   c.xh = cbase + t * 128;
   c.xl = cbase + kLineBuf + t * 128;
   c.yh = cbase + 2 * kLineBuf + t * 128;
   c.yl = cbase + 3 * kLineBuf + t * 128;
   c.sw = t & 7;
+  c.bar_dw = &bars[2 + ctx];
+  c.phase_dw = 0;
+  c.dw_pending = false;
   uint8_t* zh = cbase + 4 * kLineBuf + t * 16;
   uint8_t* zl = zh + kZBuf;
   const uint32_t s_hi = smem_u32(smem), s_lo = s_hi + kImg16 * 2;
@@ -288,7 +307,7 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
 #pragma unroll
     for (int c0 = 0; c0 < (int)fAccCols; c0 += 16) tmem_st16(acc_row + c0, z);
   }
-  mbar_wait(&bars[2], 0);  // weight images in shared memory
+  mbar_wait(&bars[4], 0);  // weight images in shared memory
 
   const int64_t n_tiles = (N + kTile - 1) / kTile;
   const int64_t tile_step = (int64_t)gridDim.x * 2;
@@ -300,7 +319,6 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
     load_tile_inputs(cur, p0, N, enc, enc_stride, views, views_stride, pts_per_view, keep, aligned);
     if (p0 < N) go_cur = __ldg(reinterpret_cast<const float4*>(dout) + p0);
   }
-  bool pending_dw0 = false;  // a dW0 group was issued after the last commit
 
   for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
     const int64_t p = tile * kTile + t;
@@ -321,9 +339,8 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
     const float4 go = go_cur;
     const float dsigma = (valid && cur.keep != 0) ? go.w : 0.f;
     // the forward pass's ReLU gates, when the caller kept them
-    const bool have_gate = gates != nullptr;
     uint64_t g1 = 0, g3 = 0, g4 = 0;
-    if (have_gate && valid) {
+    if (HAVE_GATES && valid) {
       const uint2* gp = reinterpret_cast<const uint2*>(gates + p * 6);
       const uint2 a = __ldg(gp), b = __ldg(gp + 1), d = __ldg(gp + 2);
       g1 = ((uint64_t)a.y << 32) | a.x;
@@ -334,16 +351,15 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
       issue_layer16<64, 32>(c.tmem, s_hi + bW0 * 2, s_lo + bW0 * 2);
       umma_commit(bar);
     });
-    pending_dw0 = false;
     // ---- E0: h1 = relu(.) -> A (K = 64); the packed words are kept for dW1
-    uint32_t h1hi[32], h1lo[32];
-    const uint64_t m1 = epilogue64<true, kToA, true>(c, g1, h1hi, h1lo, have_gate);
+    uint32_t h1hi[32], h1lo[32];  // h1hi: unused (the hi words live in TMEM)
+    const uint64_t m1 = epilogue64<true, HAVE_GATES, kToA, true>(c, g1, h1hi, h1lo);
     step(sync_id, leader_warp, bar, phase, [&] {
       issue_layer16<16, 64>(c.tmem, s_hi + bW1 * 2, s_lo + bW1 * 2);
       umma_commit(bar);
     });
-    // ---- E1: h2 = [sigma | geo]; c = [sh(16) | geo(15) | 0] -> A (K = 32); words kept for dW2
-    uint32_t chi[16], clo[16];
+    // ---- E1: h2 = [sigma | geo]; c = [sh(16) | geo(15) | 0] -> A (K = 32); the geo words are kept for dW2
+    uint32_t ghi[8], glo[8];
     {
       float h2[16];
       tmem_ld16(c.row + fColD, h2);
@@ -353,21 +369,11 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
       g[15] = 0.f;
       uint32_t hi[8], lo[8];
       pack16(vsh, hi, lo);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        chi[i] = hi[i];
-        clo[i] = lo[i];
-      }
       tmem_st8(c.row + fColAhi, hi);
       tmem_st8(c.row + fColAlo, lo);
-      pack16(g, hi, lo);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        chi[8 + i] = hi[i];
-        clo[8 + i] = lo[i];
-      }
-      tmem_st8(c.row + fColAhi + 8, hi);
-      tmem_st8(c.row + fColAlo + 8, lo);
+      pack16(g, ghi, glo);
+      tmem_st8(c.row + fColAhi + 8, ghi);
+      tmem_st8(c.row + fColAlo + 8, glo);
     }
     step(sync_id, leader_warp, bar, phase, [&] {
       issue_layer16<64, 32>(c.tmem, s_hi + bW2 * 2, s_lo + bW2 * 2);
@@ -375,13 +381,13 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
     });
     // ---- E2: h3 -> A (K = 64) and -> Y (N side of dW3)
     uint32_t dummy_hi[32], dummy_lo[32];
-    const uint64_t m3 = epilogue64<true, kToA | kToY, false>(c, g3, dummy_hi, dummy_lo, have_gate);
+    const uint64_t m3 = epilogue64<true, HAVE_GATES, kToA | kToY, false>(c, g3, dummy_hi, dummy_lo);
     step(sync_id, leader_warp, bar, phase, [&] {
       issue_layer16<64, 64>(c.tmem, s_hi + bW3 * 2, s_lo + bW3 * 2);
       umma_commit(bar);
     });
     // ---- E3: h4 -> X (M side of dW4); drgb -> Z and -> A (K = 16, columns 3..15 zero)
-    const uint64_t m4 = epilogue64<true, kToX, false>(c, g4, dummy_hi, dummy_lo, have_gate);
+    const uint64_t m4 = epilogue64<true, HAVE_GATES, kToX, false>(c, g4, dummy_hi, dummy_lo);
     {
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -390,40 +396,41 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
       split_bf16x2(go.z, 0.f, hi[1], lo[1]);
       tmem_st8(c.row + fColAhi, hi);
       tmem_st8(c.row + fColAlo, lo);
+      wait_dw(c);
       *reinterpret_cast<uint4*>(zh) = make_uint4(hi[0], hi[1], 0u, 0u);
       *reinterpret_cast<uint4*>(zl) = make_uint4(lo[0], lo[1], 0u, 0u);
     }
     step(sync_id, leader_warp, bar, phase, [&] {
-      issue_dw<8, true>(acc + aW4, sX_hi, sX_lo, sZ_hi, sZ_lo);                  // dW4^T += h4^T . drgb
       issue_layer16<64, 16>(c.tmem, s_hi + bT4 * 2, s_lo + bT4 * 2);            // dh4 = drgb . W4
       umma_commit(bar);
+      issue_dw<8, true>(acc + aW4, sX_hi, sX_lo, sZ_hi, sZ_lo);                  // dW4^T += h4^T . drgb
+      umma_commit(c.bar_dw);
     });
+    c.dw_pending = true;
     // ---- E4: dz4 = dh4 . [h4 > 0] -> A (K = 64) and -> X
-    epilogue64<false, kToA | kToX, false>(c, m4, dummy_hi, dummy_lo);
+    epilogue64<false, false, kToA | kToX, false>(c, m4, dummy_hi, dummy_lo);
     step(sync_id, leader_warp, bar, phase, [&] {
-      issue_dw<64, false>(acc + aW3, sX_hi, sX_lo, sY_hi, sY_lo);                // dW3 += dz4^T . h3
       issue_layer16<64, 64>(c.tmem, s_hi + bT3 * 2, s_lo + bT3 * 2);            // dh3 = dz4 . W3
       umma_commit(bar);
+      issue_dw<64, false>(acc + aW3, sX_hi, sX_lo, sY_hi, sY_lo);                // dW3 += dz4^T . h3
+      umma_commit(c.bar_dw);
     });
-    // ---- E5: dz3 -> A (K = 64) and -> X; c -> Y (32 features)
-    epilogue64<false, kToA | kToX, false>(c, m3, dummy_hi, dummy_lo);
+    c.dw_pending = true;
+    // ---- E5: dz3 -> A (K = 64) and -> X; c = [sh | geo] -> Y (32 features)
+    epilogue64<false, false, kToA | kToX, false>(c, m3, dummy_hi, dummy_lo);
     {
       uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          hi[i] = chi[8 * h + i];
-          lo[i] = clo[8 * h + i];
-        }
-        put_chunks(c.yh, c.yl, c.sw, 2 * h, hi, lo);
-      }
+      pack16(vsh, hi, lo);
+      put_chunks(c.yh, c.yl, c.sw, 0, hi, lo);
+      put_chunks(c.yh, c.yl, c.sw, 2, ghi, glo);
     }
     step(sync_id, leader_warp, bar, phase, [&] {
-      issue_dw<32, false>(acc + aW2, sX_hi, sX_lo, sY_hi, sY_lo);                // dW2 += dz3^T . c
       issue_layer16<16, 64>(c.tmem, s_hi + bT2 * 2, s_lo + bT2 * 2);            // dgeo = (dz3 . W2)[16:31]
       umma_commit(bar);
+      issue_dw<32, false>(acc + aW2, sX_hi, sX_lo, sY_hi, sY_lo);                // dW2 += dz3^T . c
+      umma_commit(c.bar_dw);
     });
+    c.dw_pending = true;
     // ---- E6: dh2 = [dsigma | dgeo] -> A (K = 16) and -> Y (16 features); h1 -> X
     {
       float dg[16], v[16];
@@ -435,33 +442,28 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
       pack16(v, hi, lo);
       tmem_st8(c.row + fColAhi, hi);
       tmem_st8(c.row + fColAlo, lo);
+      wait_dw(c);
       put_chunks(c.yh, c.yl, c.sw, 0, hi, lo);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
+        tmem_ld8w(c.stash + 8 * q, hi);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          hi[i] = h1hi[8 * q + i];
-          lo[i] = h1lo[8 * q + i];
-        }
+        for (int i = 0; i < 8; ++i) lo[i] = h1lo[8 * q + i];
         put_chunks(c.xh, c.xl, c.sw, 2 * q, hi, lo);
       }
     }
-    // the hash features again (N side of dW0, needed two steps from now) and the next tile's inputs
+    // the hash features again (N side of dW0, needed one step from now)
     float e2[32];
     load_enc_row(e2, p, N, enc, enc_stride, aligned);
-    go_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tile + tile_step < n_tiles) {
-      const int64_t pn = (tile + tile_step) * kTile + t;
-      load_tile_inputs(cur, pn, N, enc, enc_stride, views, views_stride, pts_per_view, keep, aligned);
-      if (pn < N) go_cur = __ldg(reinterpret_cast<const float4*>(dout) + pn);
-    }
     step(sync_id, leader_warp, bar, phase, [&] {
-      issue_dw<16, false>(acc + aW1, sX_hi, sX_lo, sY_hi, sY_lo);                // dW1^T += h1^T . dh2
       issue_layer16<64, 16>(c.tmem, s_hi + bT1 * 2, s_lo + bT1 * 2);            // dh1 = dh2 . W1
       umma_commit(bar);
+      issue_dw<16, false>(acc + aW1, sX_hi, sX_lo, sY_hi, sY_lo);                // dW1^T += h1^T . dh2
+      umma_commit(c.bar_dw);
     });
+    c.dw_pending = true;
     // ---- E7: dz1 -> A (K = 64) and -> X; hash features -> Y (32 features)
-    epilogue64<false, kToA | kToX, false>(c, m1, dummy_hi, dummy_lo);
+    epilogue64<false, false, kToA | kToX, false>(c, m1, dummy_hi, dummy_lo);
     {
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -473,12 +475,20 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
         put_chunks(c.yh, c.yl, c.sw, 2 * h, hi, lo);
       }
     }
+    // the next tile's inputs: in flight while T0 runs and d_enc is written
+    go_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tile + tile_step < n_tiles) {
+      const int64_t pn = (tile + tile_step) * kTile + t;
+      load_tile_inputs(cur, pn, N, enc, enc_stride, views, views_stride, pts_per_view, keep, aligned);
+      if (pn < N) go_cur = __ldg(reinterpret_cast<const float4*>(dout) + pn);
+    }
     step(sync_id, leader_warp, bar, phase, [&] {
       issue_layer16<32, 64>(c.tmem, s_hi + bT0 * 2, s_lo + bT0 * 2);            // d_enc = dz1 . W0
       umma_commit(bar);
-      issue_dw<32, false>(acc + aW0, sX_hi, sX_lo, sY_hi, sY_lo);                // dW0 += dz1^T . in (not waited for)
+      issue_dw<32, false>(acc + aW0, sX_hi, sX_lo, sY_hi, sY_lo);                // dW0 += dz1^T . in
+      umma_commit(c.bar_dw);
     });
-    pending_dw0 = true;
+    c.dw_pending = true;
     // ---- E8: d_enc out
 #pragma unroll
     for (int c0 = 0; c0 < kIn; c0 += 16) {
@@ -497,17 +507,7 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   wait_st();
   fence_before_sync();
   ctx_sync(sync_id);
-  if (pending_dw0) {
-    if (leader_warp) {
-      if (elect_one()) {
-        fence_after_sync();
-        umma_commit(bar);
-      }
-      __syncwarp();
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-  }
+  wait_dw(c);
   fence_after_sync();
   if (tile0 < n_tiles) {
     // M = 64 accumulator rows: row m sits in lane (m % 16) + 32 (m / 16) of its lane half; a thread with
@@ -551,7 +551,10 @@ int mlp_tc_bwd_fused(const float* enc, int64_t enc_stride, const float* views, i
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail((int)e, "cudaGetDevice");
   if (done_dev != dev) {
-    e = cudaFuncSetAttribute(tc::mlp_tc_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(tc::mlp_tc_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)tc::kFusedSmemBytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_fused_kernel)");
+    e = cudaFuncSetAttribute(tc::mlp_tc_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)tc::kFusedSmemBytes);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(mlp_tc_bwd_fused_kernel)");
     done_dev = dev;
@@ -564,8 +567,12 @@ int mlp_tc_bwd_fused(const float* enc, int64_t enc_stride, const float* views, i
   const int64_t cap = (int64_t)sm_count();
   const int64_t want = (tiles + 1) / 2;  // two tile contexts per CTA
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  tc::mlp_tc_bwd_fused_kernel<<<grid, 2 * tc::kTile, tc::kFusedSmemBytes, stream>>>(
-      enc, enc_stride, views, views_stride, pts_per_view, images, keep, gates, dout, N, d_enc, dweights, aligned);
+  if (gates != nullptr)
+    tc::mlp_tc_bwd_fused_kernel<true><<<grid, 2 * tc::kTile, tc::kFusedSmemBytes, stream>>>(
+        enc, enc_stride, views, views_stride, pts_per_view, images, keep, gates, dout, N, d_enc, dweights, aligned);
+  else
+    tc::mlp_tc_bwd_fused_kernel<false><<<grid, 2 * tc::kTile, tc::kFusedSmemBytes, stream>>>(
+        enc, enc_stride, views, views_stride, pts_per_view, images, keep, gates, dout, N, d_enc, dweights, aligned);
   return check_launch("mlp_tc_bwd_fused_kernel");
 }
 
