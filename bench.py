@@ -207,6 +207,73 @@ def cpu_pipeline_cfg0(steps: int = 1, warmup: int = 1):
                         "render_rays fwd + backward through the reference's own modules"}
 
 
+def reference_gpu_extra(dev, log2T=19):
+    """The reference's own PyTorch code on the SAME B200 (SURVEY 2.2 / BASELINE.md 4: the per-kernel bar is the
+    reference's chain of ATen kernels on this GPU): hash-encode fwd+bwd at 2^22 points, and the training-loop body
+    of run_nerf.py:608-642 (render_rays 64+128, mse + sparsity + 16 TV terms, backward, the reference's RAdam) at
+    N_rand 1024 and 8192.  Runs under the CUDA default tensor type exactly as run_nerf.py:725 sets it."""
+    out = {}
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    if not ref_loader.available():
+        return {"unavailable": "oracle/_ref is missing (run oracle/make_ref.py where /root/reference exists)"}
+    torch.set_default_tensor_type('torch.cuda.FloatTensor')
+    try:
+        ref = ref_loader.load("cuda")
+        lo, hi = torch.tensor(BBOX[0], device=dev), torch.tensor(BBOX[1], device=dev)
+        emb = _reference_encoder(ref, log2T, dev)
+        n = 1 << 22
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.rand(n, 3, device=dev, generator=g) * (hi - lo) + lo
+        dy = torch.randn(n, 32, device=dev, generator=g)
+
+        def enc_step():
+            for e in emb.embeddings:
+                e.weight.grad = None
+            y, _ = emb(x)
+            y.backward(dy)
+
+        ms = time_loop(enc_step, 3, 1) / 3
+        out["hash_encode_fwd_bwd_msamples_per_s"] = round(n / ms / 1e3, 2)
+        out["hash_encode_points"] = n
+        del x, dy
+        torch.cuda.empty_cache()
+
+        mk = lambda: ref.NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3,
+                                   hidden_dim_color=64, input_ch=32, input_ch_views=16).to(dev)
+        coarse, fine, sh = mk(), mk(), ref.SHEncoder()
+        opt = ref.RAdam([{"params": list(coarse.parameters()) + list(fine.parameters()), "weight_decay": 1e-6},
+                         {"params": list(emb.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+        qfn = lambda i, v, fn: ref.run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh, netchunk=1 << 16)
+        for n_rand in (1024, 8192):
+            o = torch.tensor([0., 0., 4.], device=dev) + 0.1 * torch.randn(n_rand, 3, device=dev, generator=g)
+            d = -o / o.norm(dim=-1, keepdim=True) + 0.2 * torch.randn(n_rand, 3, device=dev, generator=g)
+            rays = torch.cat([o, d, torch.full((n_rand, 1), 2., device=dev), torch.full((n_rand, 1), 6., device=dev),
+                              d / d.norm(dim=-1, keepdim=True)], -1)
+            target = torch.rand(n_rand, 3, device=dev, generator=g)
+
+            def train_step():
+                ret = ref.render_rays(rays, coarse, qfn, 64, embed_fn=emb, retraw=True, perturb=1., N_importance=128,
+                                      network_fine=fine, white_bkgd=True)
+                opt.zero_grad()
+                loss = ((ret["rgb_map"] - target) ** 2).mean() + ((ret["rgb0"] - target) ** 2).mean() \
+                    + 1e-10 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum())
+                tv = sum(ref.total_variation_loss(emb.embeddings[i], 16, 512, i, log2T, n_levels=16) for i in range(16))
+                (loss + 1e-6 * tv).backward()
+                opt.step()
+
+            ms = time_loop(train_step, 5, 2) / 5
+            out[f"train_rays_per_s_nrand{n_rand}"] = round(n_rand / ms * 1e3, 1)
+            out[f"train_ms_per_step_nrand{n_rand}"] = round(ms, 2)
+        out["what"] = ("the reference's unmodified modules (oracle/_ref) on device='cuda' of this same B200: eager ATen "
+                       "kernels, fp32, torch " + torch.__version__)
+    except Exception as exc:  # the leg is informative: never lose the bench line over it
+        out["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    finally:
+        torch.set_default_tensor_type('torch.FloatTensor')
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -237,6 +304,11 @@ def workload_config(args, n_points):
             "points_per_step_per_gpu": n_points, "log2_hashmap_size": args.log2T,
             "l2": "inputs larger than L2 (x 201 MB + dY 2.1 GB + features 2.1 GB per step); the 64 MiB table stays "
                   "L2-resident across steps, as in steady-state training",
+            "timed_path": "value: the launches HashEmbedder.forward + autograd issue for this batch, called directly "
+                          "through hn_b200.ops (sort, gather, zero-grad, scatter[, all-reduce]) on device-resident "
+                          "inputs; e2e: the same work through the public HashEmbedder API with host inputs",
+            "e2e_readback": "a training pipeline keeps features and gradients on the device: the per-step result read "
+                            "back is the 16 per-level gradient sums (64 B), not the 2.1 GB feature tensor",
             "parallelism": (f"dp{args.gpus} (points sharded; table gradient all-reduced "
                             + ("in 4 level buckets, each overlapping the next bucket's scatter" if args.bucket_overlap
                                else "once after the scatter") + ")")
@@ -358,6 +430,73 @@ def inference_frame_extra(dev, H=800, W=800, dist=None):
     return ms
 
 
+def dp_self_check(dist, dev, world, bwd, dflat, tables):
+    """N > 1, once before timing: (1) the all-reduced table gradient's checksum equals the sum of the per-rank
+    checksums gathered separately; (2) after one fused RAdam step on the reduced gradient (1/world folded in) the
+    parameters are bit-identical on every rank.  Works on copies: the timed state is untouched."""
+    from radam import RAdam
+    dflat.zero_()
+    bwd()
+    local = dflat.double().sum().reshape(1)
+    sums = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(sums, local)
+    expect = float(sum(t.item() for t in sums))
+    red = dflat.clone()
+    dist.all_reduce(red)
+    got = float(red.double().sum().item())
+    scale = float(red.double().abs().sum().item()) + 1e-30
+    ok_sum = abs(got - expect) <= 1e-6 * scale
+    p = torch.nn.Parameter(tables.detach().clone())
+    p.grad = red
+    opt = RAdam([{"params": [p], "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+    opt.grad_scale = 1.0 / world
+    opt.step()
+    h = p.detach().view(torch.int32).long().sum().reshape(1)
+    hs = [torch.zeros_like(h) for _ in range(world)]
+    dist.all_gather(hs, h)
+    ok_par = all(int(t.item()) == int(hs[0].item()) for t in hs)
+    dflat.zero_()
+    return "ok" if (ok_sum and ok_par) else f"FAILED (checksum {ok_sum}, parameters identical {ok_par})"
+
+
+def train_shape_roofline(dev, emb, peak, steps=10):
+    """The kernels the TRAINING path launches (caller-ordered ray samples, no sort, warp-aggregated scatter) at the
+    data-parallel shape: 8192 rays x (64 + 192) samples = 2,097,152 points along rays; same 1164 B/sample formula."""
+    from hn_b200 import ops
+    R, S = 8192, 256
+    g = torch.Generator(device=dev).manual_seed(3)
+    o = torch.tensor([0., 0., 4.], device=dev) + 0.1 * torch.randn(R, 3, device=dev, generator=g)
+    d = -o / o.norm(dim=-1, keepdim=True) + 0.2 * torch.randn(R, 3, device=dev, generator=g)
+    z = torch.sort(2. + 4. * torch.rand(R, S, device=dev, generator=g), -1).values
+    pts = (o[:, None, :] + d[:, None, :] * z[:, :, None]).reshape(-1, 3).contiguous()
+    n = pts.shape[0]
+    dy = torch.randn(n, 32, device=dev, generator=g)
+    tables = emb.flat_tables()
+    box, res = emb._geometry(dev)
+    dflat = torch.zeros(tables.numel(), device=dev)
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)   # > L2: the points / dY / features are evicted
+
+    def fwd():
+        flush.zero_()
+        ops.hash_encode_forward(pts, tables, box, res, 16, 2, emb.log2_hashmap_size, want_keep=True)
+
+    def bwd():
+        flush.zero_()
+        ops.hash_encode_backward(pts, dy, box, res, 16, 2, emb.log2_hashmap_size, dflat, ordered=True)
+
+    def only_flush():
+        flush.zero_()
+
+    t_flush = time_loop(only_flush, steps, 2) / steps
+    t_f = time_loop(fwd, steps, 2) / steps - t_flush
+    t_b = time_loop(bwd, steps, 2) / steps - t_flush
+    gb_f, gb_b = n * BYTES_PER_SAMPLE_FWD / t_f / 1e6, n * BYTES_PER_SAMPLE_BWD / t_b / 1e6
+    return {"points": n, "shape": "8192 rays x (64 + 192) samples, ray order (hn_hash_encode_fwd / _bwd_ordered)",
+            "l2": "192 MiB written between launches (its time subtracted)",
+            "fwd": {"ms": round(t_f, 4), "gbs": round(gb_f, 1), "frac": round(gb_f / peak, 4)},
+            "bwd": {"ms": round(t_b, 4), "gbs": round(gb_b, 1), "frac": round(gb_b / peak, 4)}, "peak": peak, "unit": "GB/s"}
+
+
 def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
@@ -424,6 +563,11 @@ def run_ours(args):
                 reducer.reduce_levels(dflat, b, e)
             reducer.wait()
 
+    dp_check = None
+    if dist is not None:
+        out_holder["xs4"] = ops.hash_sort_points(x, box, grid_res)
+        dp_check = dp_self_check(dist, dev, world, bwd, dflat, tables)
+
     # ---- headline: device-resident inputs
     clocks = ClockSampler(local)
     launches0 = _lib.launches
@@ -457,7 +601,10 @@ def run_ours(args):
                 "sort": {"ms": round(sort_ms, 4), "grid_res": grid_res,
                          "note": "counting sort of the points by grid cell; 5 small kernels, counted in the step"},
                 "step_frac_of_hbm": round(n * (BYTES_PER_SAMPLE_FWD + BYTES_PER_SAMPLE_BWD)
-                                          / (sort_ms + fwd_ms + bwd_ms) / 1e6 / peak, 4)}
+                                          / (sort_ms + fwd_ms + bwd_ms) / 1e6 / peak, 4),
+                "traffic_source": "profiles/traffic.json (dram__bytes_read + write per launch from the ncu --set full "
+                                  "capture of this build; not re-measured in this run)"}
+    roofline_train = train_shape_roofline(dev, emb, peak, steps=max(5, args.steps // 2)) if rank == 0 else None
 
     # ---- end to end through the public API with host inputs
     # The user-level pattern for host-resident points (a data loader with one step of prefetch): every step
@@ -601,6 +748,8 @@ def run_ours(args):
         ms = inference_frame_extra(dev)
         extra["inference_800x800_ms_per_frame"] = round(ms, 2)
         extra["inference_800x800_mrays_per_s"] = round(0.64 / ms * 1e3, 2)
+        torch.cuda.empty_cache()
+        extra["reference_gpu"] = reference_gpu_extra(dev, log2T)
         extra["train_step"] = ("render_rays 64+128 samples/ray, perturb=1, white_bkgd, mse+sparsity, backward, RAdam"
                                "; eager = the drop-in API driven like run_nerf.py:608-642 incl. the 16 TV-loss terms, cuda_graph "
                                "= hn_b200.graph.GraphedTrainStep replaying render+loss+backward+RAdam (no TV)")
@@ -617,8 +766,10 @@ def run_ours(args):
     line = {"metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "clocks": clock_report, "extra": extra}
+            "roofline": roofline, "roofline_train": roofline_train, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(gpu_launches), "clocks": clock_report, "extra": extra}
+    if dp_check is not None:
+        line["dp_check"] = dp_check
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -23,19 +23,30 @@ from . import ops
 class GraphedTrainStep:
     def __init__(self, n_rays: int, render_fn: Callable[[torch.Tensor], dict], loss_fn: Callable[[dict, torch.Tensor], torch.Tensor],
                  optimizer, device, ray_width: int = 11, warmup: int = 3, lr_schedule: Optional[Callable[[int], float]] = None,
-                 grad_sync: Optional[Callable[[], None]] = None):
+                 grad_sync: Optional[Callable[[], None]] = None, batcher=None, fused_zero_grad: bool = True):
         """render_fn(ray_batch[n_rays, ray_width]) -> dict (e.g. a closure over render_rays);
         loss_fn(ret, target[n_rays,3]) -> scalar; optimizer: radam.RAdam.  ``warmup`` eager steps are real
         optimisation steps (they also initialise the optimizer state and every lazy allocation).
         ``grad_sync``: called between backward and the optimizer, eagerly and inside the capture -- data-parallel
         runs pass ``dp.GradSync(...).all_reduce_inline`` (NCCL collectives on the capturing stream become graph
-        nodes) and set ``optimizer.grad_scale = 1 / world_size``."""
+        nodes) and set ``optimizer.grad_scale = 1 / world_size``.
+        ``batcher``: a ``batcher.DeviceRayBatcher``; ``step()`` then takes no arguments and the pixel sampling / ray
+        generation / target gather launch is part of the captured graph.
+        ``fused_zero_grad``: the optimizer pass also clears the gradients it consumed (radam.RAdam.fused_zero_grad),
+        so neither the eager warm-up steps nor the graph contain a separate 64 MiB fill of the table gradient."""
         self._grad_sync = grad_sync
+        self._batcher = batcher
         self.opt = optimizer
+        if fused_zero_grad and hasattr(optimizer, "fused_zero_grad"):
+            optimizer.fused_zero_grad = True
         self.lr_schedule = lr_schedule
         self.global_step = 0
         self.rays = torch.zeros(n_rays, ray_width, device=device)
         self.target = torch.zeros(n_rays, 3, device=device)
+        if batcher is not None:    # the batcher's launch writes straight into the graph's static buffers
+            if batcher.n_rand != n_rays:
+                raise RuntimeError("batcher.n_rand must equal n_rays")
+            batcher.rays, batcher.target = self.rays, self.target
         self._render, self._loss = render_fn, loss_fn
         self._warmup = warmup
         self.graph = None
@@ -56,37 +67,56 @@ class GraphedTrainStep:
             for g in self.opt.param_groups:
                 g['lr'] = lr
 
-    def step(self, rays: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        """One optimisation step on (rays, target); returns the (device) loss of this step."""
-        self.rays.copy_(rays, non_blocking=True)
-        self.target.copy_(target, non_blocking=True)
+    def _fill(self):
+        """This step's rays and targets into the static buffers (batcher launch: also what the graph replays)."""
+        rays, target = self._batcher.launch()
+        if rays.data_ptr() != self.rays.data_ptr():
+            self.rays.copy_(rays, non_blocking=True)
+            self.target.copy_(target, non_blocking=True)
+
+    def step(self, rays: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step on (rays, target) -- or on the batcher's next draw; returns the (device) loss."""
+        if self._batcher is not None:
+            self._batcher.prepare()
+        else:
+            self.rays.copy_(rays, non_blocking=True)
+            self.target.copy_(target, non_blocking=True)
         self._set_lr()
         self.global_step += 1
-        if self.graph is None and self._warmup > 0:
-            self._warmup -= 1
-            self.loss = self._eager().detach()
-            return self.loss
         if self.graph is None:
-            self._capture()
+            if self._batcher is not None:
+                self._fill()
+            if self._warmup > 0:
+                self._warmup -= 1
+                self.loss = self._eager().detach()
+            else:
+                self.loss = self._capture()   # the eager step inside IS this call's optimisation step
+            return self.loss
         self.opt.graph_prepare()
         self.graph.replay()
         ops.param_epoch[0] += 1
         return self.loss
 
     def _capture(self):
+        """One last eager step (on a side stream, so that every lazy allocation and the optimizer's span plan
+        exist), then the capture.  Capturing executes nothing: this batch is applied exactly once and the
+        optimizer's step counters stay in lockstep with ``global_step``."""
         side = torch.cuda.Stream(device=self.rays.device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):      # one more eager step on the side stream so gradients exist for the plan
-            self._eager()
+        with torch.cuda.stream(side):
+            eager_loss = self._eager().detach()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.opt.graph_plan()
         self.opt.zero_grad(set_to_none=True)   # the captured backward must start with "no gradient yet"
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
+            if self._batcher is not None:
+                self._fill()
             loss = self._loss(self._render(self.rays), self.target)
             loss.backward()
             if self._grad_sync is not None:
                 self._grad_sync()
             self.opt.graph_launch()
             self.loss = loss.detach()
+        return eager_loss

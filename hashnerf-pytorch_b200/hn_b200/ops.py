@@ -609,6 +609,44 @@ def get_rays_d(H: int, W: int, fx: float, fy: float, cx: float, cy: float, c2w: 
     return out
 
 
+def ndc_rays(H: int, W: int, focal: float, near: float, rays_o: torch.Tensor, rays_d: torch.Tensor):
+    """ray_util.py:96-142 in one launch: (rays_o, rays_d) [..., 3] -> NDC (o, d), same leading shape."""
+    dev = _need_cuda(rays_o, rays_d)
+    shape = rays_d.shape
+    o, o_stride = _rows3(rays_o.reshape(-1, 3))
+    d, d_stride = _rows3(rays_d.reshape(-1, 3))
+    R = d.shape[0]
+    out_o = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    out_d = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.call("hn_ndc_rays", int(H), int(W), float(focal), float(near), o.data_ptr(), o_stride, d.data_ptr(),
+                  d_stride, R, out_o.data_ptr(), out_d.data_ptr(), _stream())
+    return out_o.reshape(shape), out_d.reshape(shape)
+
+
+def sample_rays(images: torch.Tensor, poses: torch.Tensor, H: int, W: int, K, near: float, far: float,
+                step_params: torch.Tensor, n_rand: int, rays: Optional[torch.Tensor] = None,
+                target: Optional[torch.Tensor] = None, want_pix: bool = False):
+    """hn_sample_rays: images [n_img,H,W,C>=3] fp32 and poses [n_img,3,4] fp32 resident on the device;
+    step_params int32[6] on the device = (image index, seed, row0, col0, win_h, win_w).  Returns
+    (rays [n_rand,11], target [n_rand,3][, pix [n_rand,2] int32])."""
+    dev = _need_cuda(images, poses, step_params)
+    if images.dtype != torch.float32 or not images.is_contiguous() or images.dim() != 4 or images.shape[1:3] != (H, W):
+        raise RuntimeError("images must be a contiguous fp32 [n_img, H, W, C] tensor")
+    if poses.dtype != torch.float32 or not poses.is_contiguous() or poses.shape[1:] != (3, 4):
+        raise RuntimeError("poses must be a contiguous fp32 [n_img, 3, 4] tensor")
+    if step_params.dtype != torch.int32 or step_params.numel() < 6:
+        raise RuntimeError("step_params must be int32[6] on the device")
+    rays = torch.empty(n_rand, 11, dtype=torch.float32, device=dev) if rays is None else rays
+    target = torch.empty(n_rand, 3, dtype=torch.float32, device=dev) if target is None else target
+    pix = torch.empty(n_rand, 2, dtype=torch.int32, device=dev) if want_pix else None
+    with _on(dev):
+        _lib.call("hn_sample_rays", images.data_ptr(), int(images.shape[3]), poses.data_ptr(), int(H), int(W),
+                  float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), float(near), float(far),
+                  step_params.data_ptr(), int(n_rand), rays.data_ptr(), target.data_ptr(), _ptr(pix), _stream())
+    return (rays, target, pix) if want_pix else (rays, target)
+
+
 def _rows3(t: torch.Tensor):
     if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
         t = t.float().contiguous()

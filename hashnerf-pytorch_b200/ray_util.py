@@ -1,14 +1,34 @@
 """Ray generation -- drop-in for the functions of the reference's ``ray_util.py`` that ``run_nerf.py`` and
-``render`` use (get_rays :62-80, get_rays_np :82-93, get_ndc_rays :96-142).
+``render`` use (get_rays :62-80, get_rays_np :82-93, get_ndc_rays :96-142), plus the two helpers its ``bbox.py``
+imports from this module (get_directions :8-33, ray_from_directions :35-60).
 
-These feed the hot path but are not on it ("next" row 3).  ``get_rays`` on a CUDA pose is one
-kernel launch (hn_get_rays); the numpy variant and the NDC warp stay plain array math.  The kornia-based equirectangular helpers (ray_util.py:8-57) serve the st3d branch, which is
+These feed the hot path but are not on it ("next" row 3).  ``get_rays`` on a CUDA pose and
+``get_ndc_rays`` on CUDA rays are one kernel launch each (hn_get_rays, hn_ndc_rays); the numpy variant and CPU
+tensors stay plain array math.  The kornia-based equirectangular helpers (ray_util.py:8-57) serve the st3d branch, which is
 dead in the reference (Appendix B6), and are not provided.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
+
+
+def get_directions(H, W, focal):
+    """Ray directions of all pixels in the camera frame, [H, W, 3] on the CPU (ray_util.py:8-33; used by the
+    reference's bbox.py, which run_nerf.py's Blender / LLFF loaders call).  The reference builds the pixel grid
+    with kornia.create_meshgrid, i.e. CPU linspaces whatever the default tensor type is."""
+    xs = torch.linspace(0, W - 1, W, device="cpu", dtype=torch.float32)
+    ys = torch.linspace(0, H - 1, H, device="cpu", dtype=torch.float32)
+    j, i = torch.meshgrid(ys, xs, indexing="ij")
+    return torch.stack([(i - W / 2) / focal, -(j - H / 2) / focal, -torch.ones_like(i)], -1)
+
+
+def ray_from_directions(directions, c2w):
+    """World-space origins and NORMALISED directions of all pixels, each [H*W, 3] (ray_util.py:35-60)."""
+    rays_d = directions @ c2w[:3, :3].T
+    rays_d = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
 
 
 def get_rays(H, W, K, c2w):
@@ -36,7 +56,12 @@ def get_rays_np(H, W, K, c2w):
 
 
 def get_ndc_rays(H, W, focal, near, rays_o, rays_d):
-    """Forward-facing scenes: move origins to the near plane and map to normalised device coordinates."""
+    """Forward-facing scenes: move origins to the near plane and map to normalised device coordinates.
+    CUDA rays with a scalar near plane: one launch (hn_ndc_rays), bit-identical to the chain below."""
+    if isinstance(rays_d, torch.Tensor) and rays_d.is_cuda and isinstance(near, (int, float)) \
+            and rays_o.shape == rays_d.shape:
+        from hn_b200 import ops
+        return ops.ndc_rays(H, W, focal, near, rays_o, rays_d)
     t = -(near + rays_o[..., 2]) / rays_d[..., 2]
     rays_o = rays_o + t[..., None] * rays_d
     ox_oz = rays_o[..., 0] / rays_o[..., 2]

@@ -200,6 +200,21 @@ HN_API int hn_pack_rays(const float* rays_o, int64_t o_stride, const float* rays
                         const float* viewdirs, int64_t vd_stride, float near, float far, int64_t R, float* out,
                         void* stream);
 
+/* ray_util.py:96-142 (get_ndc_rays): shift the origins to the near plane and map (o, d) to normalised device
+ * coordinates; rows of rays_o / rays_d have the given strides (floats); out_o / out_d are dense [R,3].  focal and
+ * near are doubles: the reference folds them into python-float scalars before ATen rounds them. */
+HN_API int hn_ndc_rays(int H, int W, double focal, double near, const float* rays_o, int64_t o_stride,
+                       const float* rays_d, int64_t d_stride, int64_t R, float* out_o, float* out_d, void* stream);
+/* Opt-in on-device training batcher replacing run_nerf.py:576-605 + run_nerf_helpers.py:344-366: n_rand DISTINCT
+ * pixels (a keyed Feistel permutation, i.e. sampling without replacement like np.random.choice at :600) of a window
+ * of image `step[0]`; writes rays [n_rand,11] = (o, d, near, far, d/|d|) with the ray arithmetic of hn_get_rays /
+ * hn_pack_rays, target [n_rand,3] = images[img,row,col,0:3], and (pix != NULL) the chosen (row, col) pairs.
+ * images [n_img,H,W,channels] and poses [n_img,3,4] stay resident on the device; step = int32[6] ON THE DEVICE
+ * {image index, seed, row0, col0, win_h, win_w} so that the launch can be captured in a CUDA graph. */
+HN_API int hn_sample_rays(const float* images, int channels, const float* poses, int H, int W, float fx, float fy,
+                          float cx, float cy, float near, float far, const int32_t* step, int64_t n_rand,
+                          float* rays, float* target, int32_t* pix, void* stream);
+
 /* ---- section 8f "next" row 2: total_variation_loss : loss.py:11-43 ---------------------------------- */
 /* One hash level: table [2^log2T, F]; origin = int64[3] on the device (the random cube corner drawn at
  * loss.py:25); cube = cube size (loss.py:22).  fwd writes out[0] = (sum of squared forward differences over the

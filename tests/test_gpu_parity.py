@@ -763,9 +763,52 @@ def test_get_rays_golden(golden):
     bit_equal(d, g["rays_d"])                                      # same roundings as the reference's chain
     bit_equal(o.contiguous(), g["rays_o"])
     of, df = get_rays(H, W, K, g32(g["c2w_f"]))
-    no, nd = get_ndc_rays(H, W, K[0][0], 1., of.reshape(-1, 3), df.reshape(-1, 3))
-    close(no, g["ndc_o"], 2e-6, atol=1e-6)
-    close(nd, g["ndc_d"], 2e-6, atol=1e-6)
+    no, nd = get_ndc_rays(H, W, K[0][0], 1., of.reshape(-1, 3), df.reshape(-1, 3))   # hn_ndc_rays
+    bit_equal(no, g["ndc_o"])
+    bit_equal(nd, g["ndc_d"])
+    no2, nd2 = get_ndc_rays(H, W, K[0][0], 1., of, df)                               # [H,W,3] in, [H,W,3] out
+    bit_equal(no2.reshape(-1, 3), g["ndc_o"])
+    bit_equal(nd2.reshape(-1, 3), g["ndc_d"])
+
+
+@pytest.mark.parametrize("n_rand,crop", [(1024, False), (300, True), (37 * 53, False)])
+def test_sample_rays_device_batcher(n_rand, crop):
+    """hn_sample_rays (opt-in replacement of run_nerf.py:576-605 + run_nerf_helpers.py:344-366): n_rand DISTINCT
+    pixels inside the window; the packed rays are bit-identical to get_rays + pack_rays at those pixels and the
+    targets are the image values there."""
+    from ray_util import get_rays
+    from hn_b200 import ops
+    from hn_b200.batcher import DeviceRayBatcher
+    H, W, focal, n_img = 37, 53, 61.5, 5
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    rs = np.random.RandomState(9)
+    images = rs.rand(n_img, H, W, 3).astype(np.float32)
+    poses = np.stack([np.concatenate([_pose(10 + i), np.array([[0, 0, 0, 1]], np.float32)], 0) for i in range(n_img)])
+    b = DeviceRayBatcher(images, poses, H, W, K, 2.0, 6.0, n_rand, DEV, i_train=[1, 3, 4],
+                         precrop_iters=5 if crop else 0, precrop_frac=0.8, seed=4)
+    seen_images, first = set(), None
+    for _ in range(3):
+        rays, target, pix = b.next(want_pix=True)
+        torch.cuda.synchronize()
+        img = int(b._dev[0].item())
+        seen_images.add(img)
+        assert img in (1, 3, 4)
+        row0, col0, wh, ww = b.window(b.step_index - 1)
+        p = pix.cpu().numpy().astype(np.int64)
+        assert len({(int(r), int(c)) for r, c in p}) == n_rand, "pixels must be distinct (sampling without replacement)"
+        assert p[:, 0].min() >= row0 and p[:, 0].max() < row0 + wh and p[:, 1].min() >= col0 and p[:, 1].max() < col0 + ww
+        o_all, d_all = get_rays(H, W, K, g32(poses[img, :3, :4]))
+        sel_d = d_all[p[:, 0], p[:, 1]]
+        sel_o = o_all[p[:, 0], p[:, 1]]
+        want = ops.pack_rays(sel_o.contiguous(), sel_d.contiguous(), sel_d.contiguous(), 2.0, 6.0)
+        bit_equal(rays, want)
+        bit_equal(target, images[img][p[:, 0], p[:, 1]])
+        if first is None:
+            first = p.copy()
+        else:
+            assert not np.array_equal(first, p), "a new permutation every step"
+    if n_rand == H * W:   # a full permutation of the image
+        assert sorted(map(tuple, p.tolist())) == [(r, c) for r in range(H) for c in range(W)]
 
 
 def test_render_ndc_forward_facing_against_oracle(monkeypatch):
@@ -847,6 +890,48 @@ def test_render_full_image_against_oracle():
 
 
 # ---------------------------------------------------------------------------------------------- next rows
+def test_radam_fused_zero_grad_and_plan_invalidation():
+    """(1) fused_zero_grad=True: same parameters as the plain optimizer, gradients read zero after step(), and the
+    hash-table gradient sink skips its own fill on the next backward yet accumulates correctly.  (2) load_state_dict /
+    add_param_group drop the cached span plan: a later lr change reaches the kernel and moments that are no longer
+    one allocation are not run over as one span (radam.py:66)."""
+    from radam import RAdam
+    torch.manual_seed(0)
+    emb_a, _ = make_embedder(cases.BBOX_UNIT, 10, scale=3000.0)
+    emb_b, _ = make_embedder(cases.BBOX_UNIT, 10, scale=3000.0)
+    opt_a = RAdam([{"params": list(emb_a.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+    opt_b = RAdam([{"params": list(emb_b.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99), fused_zero_grad=True)
+    x = g32(cases.points_in_box(3000, cases.BBOX_UNIT, seed=3))
+    for step in range(7):   # crosses RAdam's rectification switch at step 6
+        dy = torch.randn(3000, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(step))
+        for emb, opt in ((emb_a, opt_a), (emb_b, opt_b)):
+            opt.zero_grad()
+            emb(x)[0].backward(dy)
+            opt.step()
+        assert float(emb_b.grad_sink().flat.abs().max()) == 0.0 and emb_b.grad_sink().clean
+        assert float(emb_a.grad_sink().flat.abs().max()) > 0.0
+        # same trajectory (not bit for bit: the scatter's atomic accumulation order differs from run to run)
+        close(emb_b.flat_tables(), emb_a.flat_tables(), 1e-5, atol=1e-7)
+    # (2) resume from a state dict whose moments are SEPARATE allocations (what a reference checkpoint holds)
+    sd = opt_a.state_dict()
+    sd = {"state": {k: {kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} for k, v in sd["state"].items()},
+          "param_groups": sd["param_groups"]}
+    opt_a.load_state_dict(sd)
+    assert "_span_cache" not in opt_a.__dict__
+    for grp in opt_a.param_groups:
+        grp["lr"] = 0.0            # must reach the kernel: with a stale plan the old group dict (lr 0.01) would be used
+    before = emb_a.flat_tables().clone()
+    opt_a.zero_grad()
+    emb_a(x)[0].backward(torch.ones(3000, 32, device=DEV))
+    opt_a.step()
+    torch.cuda.synchronize()
+    bit_equal(emb_a.flat_tables(), before)
+    m = [opt_a.state[p]["exp_avg"] for p in emb_a.parameters()]
+    assert all(bool(torch.isfinite(t_).all()) for t_ in m)
+    opt_a.add_param_group({"params": [torch.nn.Parameter(torch.zeros(4, device=DEV))]})
+    assert "_span_cache" not in opt_a.__dict__
+
+
 def test_radam_golden(golden):
     from radam import RAdam
     g = golden("radam")

@@ -225,3 +225,64 @@ def test_rays(golden):
     no2, nd2 = get_ndc_rays(H, W, K[0][0], 1., of.reshape(-1, 3), df.reshape(-1, 3))
     assert_bit_exact(no2, g["ndc_o"])
     assert_bit_exact(nd2, g["ndc_d"])
+
+
+def test_reference_written_checkpoint_loads_into_our_modules(tmp_path):
+    """A ``.tar`` written by the reference's OWN HashEmbedder / NeRFSmall / RAdam (run_nerf.py:663-680 format) loads
+    into this repository's modules: same keys, shapes and values; the optimizer state keeps its moments and step
+    counts.  (state_dict loading needs no GPU.)"""
+    import sys
+    import os
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_loader
+    if not ref_loader.available():
+        import pytest
+        pytest.skip("reference tree not available here")
+    ref = ref_loader.load("cpu")
+    from embedding.hash_encoding import HashEmbedder
+    from models import NeRFSmall
+    from radam import RAdam
+    box = (torch.tensor([-1.5, -1.5, -1.5]), torch.tensor([1.5, 1.5, 1.5]))
+    torch.manual_seed(3)
+    r_emb = ref.HashEmbedder(box, log2_hashmap_size=10)
+    geo = dict(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64, input_ch=32,
+               input_ch_views=16)
+    r_net, r_fine = ref.NeRFSmall(**geo), ref.NeRFSmall(**geo)
+    groups = lambda emb, a, b: [{"params": list(a.parameters()) + list(b.parameters()), "weight_decay": 1e-6},
+                                {"params": list(emb.parameters()), "eps": 1e-15}]
+    r_opt = ref.RAdam(groups(r_emb, r_net, r_fine), lr=0.01, betas=(0.9, 0.99))
+    for _ in range(3):   # give the optimizer real state
+        y, _keep = r_emb(torch.rand(50, 3) * 3 - 1.5)
+        out = r_net(torch.cat([y, torch.rand(50, 16)], -1)) + r_fine(torch.cat([y, torch.rand(50, 16)], -1))
+        r_opt.zero_grad()
+        out.square().mean().backward()
+        r_opt.step()
+    path = os.path.join(tmp_path, "000003.tar")
+    torch.save({"global_step": 3, "network_fn_state_dict": r_net.state_dict(),
+                "network_fine_state_dict": r_fine.state_dict(), "embed_fn_state_dict": r_emb.state_dict(),
+                "optimizer_state_dict": r_opt.state_dict()}, path)
+
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    emb = HashEmbedder(box, log2_hashmap_size=10)
+    net, fine = NeRFSmall(**geo), NeRFSmall(**geo)
+    opt = RAdam(groups(emb, net, fine), lr=0.01, betas=(0.9, 0.99))
+    opt._span_cache = ("stale", [])          # a plan from before the resume must not survive it
+    emb.load_state_dict(ckpt["embed_fn_state_dict"])
+    net.load_state_dict(ckpt["network_fn_state_dict"])
+    fine.load_state_dict(ckpt["network_fine_state_dict"])
+    opt.load_state_dict(ckpt["optimizer_state_dict"])
+    assert "_span_cache" not in opt.__dict__
+    for a, b in zip(list(emb.parameters()) + list(net.parameters()) + list(fine.parameters()),
+                    list(r_emb.parameters()) + list(r_net.parameters()) + list(r_fine.parameters())):
+        assert a.shape == b.shape and torch.equal(a.detach(), b.detach())
+    for ours_p, ref_p in zip([p for g in opt.param_groups for p in g["params"]],
+                             [p for g in r_opt.param_groups for p in g["params"]]):
+        so, sr = opt.state[ours_p], r_opt.state[ref_p]
+        assert so["step"] == sr["step"] == 3
+        assert torch.equal(so["exp_avg"], sr["exp_avg"]) and torch.equal(so["exp_avg_sq"], sr["exp_avg_sq"])
+    assert opt.param_groups[0]["weight_decay"] == 1e-6 and opt.param_groups[1]["eps"] == 1e-15
+    # and the other way round: what we save has the reference's keys and loads into the reference's modules
+    r_emb.load_state_dict(emb.state_dict())
+    r_net.load_state_dict(net.state_dict())
+    r_opt.load_state_dict(opt.state_dict())
