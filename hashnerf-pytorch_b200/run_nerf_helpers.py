@@ -35,6 +35,10 @@ to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 DEBUG = False
+# create_nerf's RAdam clears the gradients it consumed in its own pass over memory, so that the
+# ``optimizer.zero_grad()`` of the next iteration (run_nerf.py:612) has no 64 MiB buffer left to fill.  Invisible to
+# run_nerf.py (it never reads .grad after step()); set to False for gradients that survive step().
+FUSED_ZERO_GRAD = True
 
 
 # ----------------------------------------------------------------------------------------------
@@ -133,7 +137,8 @@ def create_nerf(args):
 
     if args.i_embed == 1:
         optimizer = RAdam([{'params': grad_vars, 'weight_decay': 1e-6},
-                           {'params': embedding_params, 'eps': 1e-15}], lr=args.lrate, betas=(0.9, 0.99))
+                           {'params': embedding_params, 'eps': 1e-15}], lr=args.lrate, betas=(0.9, 0.99),
+                          fused_zero_grad=FUSED_ZERO_GRAD)
     else:
         optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
 
@@ -392,7 +397,7 @@ def _save_figure(filename, rgb8, depth01):
         import matplotlib
         matplotlib.use("Agg")
         import matplotlib.pyplot as plt
-    except ImportError:  # matplotlib is optional here: fall back to a side-by-side PNG via PIL
+    except (ImportError, AttributeError):  # no (usable) matplotlib: fall back to a side-by-side PNG via PIL
         from PIL import Image
         d8 = to8b(np.repeat(depth01[..., None], 3, axis=-1))
         Image.fromarray(np.concatenate([rgb8, d8], axis=1)).save(filename)
