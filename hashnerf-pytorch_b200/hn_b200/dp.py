@@ -12,6 +12,11 @@ T = 2^19), so the only exchange step is one summed all-reduce of the gradients p
 
 Plumbing only: ``torch.distributed`` (NCCL on GPUs; the unit tests drive the same code over gloo on CPU
 tensors with world_size 2).
+
+``FusedExchange`` is the other form of the same step: parameters and gradients live in symmetric memory and one
+kernel per flat buffer (csrc/dp_exchange.cu) reduces the gradients through the NVSwitch (multimem.ld_reduce) or over
+peer NVLink loads, applies RAdam to the rank's 1/world slice with sharded moments, multicasts the new parameters and
+clears the gradients -- collective, optimizer and zero_grad in a single pass.
 """
 from __future__ import annotations
 
@@ -122,6 +127,201 @@ class GradSync:
         self.calls_last = len(flats)
         for f in flats:
             dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group)
+
+
+class SymmetricBuffer:
+    """A flat fp32 buffer allocated identically on every rank with peer (and, on NVSwitch systems, multicast)
+    mappings.  torch.distributed._symmetric_memory does the allocation and the handle exchange; this package only
+    takes the raw pointers from it."""
+
+    def __init__(self, numel: int, device, group=None, dtype=torch.float32):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        try:  # torch < 2.8 wants the group announced first; newer versions do it in rendezvous
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.tensor = symm.empty(int(numel), dtype=dtype, device=device)
+        self.tensor.zero_()
+        self.handle = symm.rendezvous(self.tensor, group=group)
+        self.rank, self.world = int(self.handle.rank), int(self.handle.world_size)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = getattr(self.handle, "multicast_ptr", 0) or 0
+        self.multicast_ptr = int(mc) if getattr(self.handle, "has_multicast_support", lambda: bool(mc))() else 0
+        self.itemsize = self.tensor.element_size()
+
+    def ptr_table(self, offset_elems: int = 0) -> torch.Tensor:
+        """int64 device tensor of the `world` peer pointers to element ``offset_elems`` of the buffer."""
+        off = int(offset_elems) * self.itemsize
+        return torch.tensor([p + off for p in self.peer_ptrs], dtype=torch.int64, device=self.tensor.device)
+
+    def mc_ptr(self, offset_elems: int = 0) -> int:
+        return (self.multicast_ptr + int(offset_elems) * self.itemsize) if self.multicast_ptr else 0
+
+
+class FusedExchange:
+    """Gradient exchange + optimizer + zero_grad as one pass over peer memory (csrc/dp_exchange.cu).
+
+        fx = FusedExchange(optimizer, [emb, coarse, fine])      # once, after building the model on every rank
+        ...
+        loss.backward()          # gradients accumulate in the symmetric buffer (the modules' GradSinks point there)
+        fx.step()                # replaces  sync.all_reduce(); sync.wait(); optimizer.step(); optimizer.zero_grad()
+
+    ``modules``: a HashEmbedder and NeRFSmall networks (anything with ``_level_weights()`` / ``_weights()`` and a
+    flat gradient sink).  Their parameters are re-homed, in order, into ONE symmetric parameter buffer and their
+    gradient sinks into ONE symmetric gradient buffer; hyper-parameters (lr, betas, eps, weight_decay) are read from
+    the optimizer's param groups every step, so the lr schedule run_nerf.py applies to them keeps working, but
+    ``optimizer.step()`` / ``zero_grad()`` are not called any more.  The moments are SHARDED: each rank keeps
+    exp_avg / exp_avg_sq only for the slice of every buffer it owns (``gather_moments()`` collects them for a
+    checkpoint).  Parameters come out bit-identical on every rank: each slice is computed once, by its owner."""
+
+    _RING = 4
+
+    def __init__(self, optimizer, modules, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("FusedExchange needs an initialised torch.distributed process group (NCCL)")
+        self.opt = optimizer
+        self.group = group
+        spans = []
+        for mod in modules:
+            ws = mod._level_weights() if hasattr(mod, "_level_weights") else mod._weights()
+            if hasattr(mod, "_flatten_parameters"):
+                mod._flatten_parameters()
+            if not ops._consecutive(ws):
+                raise RuntimeError("module parameters are not one flat buffer")
+            spans.append((mod, ws, sum(w.numel() for w in ws)))
+        dev = spans[0][1][0].device
+        offs, total = [], 0
+        for _m, _ws, n in spans:
+            if n % 4:
+                raise RuntimeError("flat parameter buffers must be multiples of 4 floats")
+            offs.append(total)
+            total += n
+        self.params_sym = SymmetricBuffer(total, dev, group)
+        self.grads_sym = SymmetricBuffer(total, dev, group)
+        self.signals = SymmetricBuffer(256, dev, group, dtype=torch.int32)
+        self.rank, self.world = self.params_sym.rank, self.params_sym.world
+        self.multicast = bool(self.params_sym.multicast_ptr and self.grads_sym.multicast_ptr)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._spans, self._sinks = [], []
+        with torch.no_grad():
+            for (mod, ws, n), off in zip(spans, offs):
+                flat_p = self.params_sym.tensor[off:off + n]
+                flat_g = self.grads_sym.tensor[off:off + n]
+                o = 0
+                for w in ws:                                   # re-home the parameters (Parameter identity kept)
+                    view = flat_p[o:o + w.numel()].view_as(w)
+                    view.copy_(w)
+                    w.data = view
+                    o += w.numel()
+                sink = mod.grad_sink() if hasattr(mod, "grad_sink") else None
+                if sink is None:
+                    if getattr(mod, "_sink", None) is None or any(a is not b for a, b in zip(mod._sink.params, ws)):
+                        mod._sink = ops.GradSink(ws)
+                    sink = mod._sink
+                sink.adopt(flat_g)
+                self._sinks.append(sink)
+                gi = next(i for i, g in enumerate(optimizer.param_groups) if any(p is ws[0] for p in g['params']))
+                self._spans.append(dict(off=off, n=n, group=gi, step=0,
+                                        g_tab=self.grads_sym.ptr_table(off), p_tab=self.params_sym.ptr_table(off),
+                                        g_mc=self.grads_sym.mc_ptr(off), p_mc=self.params_sym.mc_ptr(off)))
+        self._sig_tab = self.signals.ptr_table(0)
+        self._hp_dev = torch.zeros(len(self._spans), 8, dtype=torch.float32, device=dev)
+        self._hp_host = [torch.zeros(len(self._spans), 8, dtype=torch.float32).pin_memory() for _ in range(self._RING)]
+        self._events = [None] * self._RING
+        self._slot = 0
+        self._epoch = 0
+        dist.barrier(group=group)          # every rank's buffers are initialised before anybody exchanges
+        torch.cuda.synchronize(dev)
+
+    def _prepare(self):
+        slot = self._slot
+        self._slot = (slot + 1) % self._RING
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()
+        host = self._hp_host[slot]
+        for i, sp in enumerate(self._spans):
+            grp = self.opt.param_groups[sp['group']]
+            sp['step'] += 1
+            beta1, beta2 = grp['betas']
+            mode, step_size = self.opt._rectification(sp['step'], beta1, beta2)
+            row = host[i]
+            row[0], row[1], row[2] = beta1, beta2, grp['eps']
+            row[3] = grp['weight_decay'] * grp['lr']
+            row[4] = step_size * grp['lr']
+            row[5], row[6], row[7] = 1.0 / self.world, float(mode), 0.0
+        self._hp_dev.copy_(host, non_blocking=True)
+        ev = self._events[slot] or torch.cuda.Event()
+        ev.record()
+        self._events[slot] = ev
+
+    def _barrier(self, slot: int):
+        _lib_call("hn_dp_barrier", self._sig_tab.data_ptr(), self.rank, self.world, slot, self._epoch, ops._stream())
+
+    def step(self):
+        """barrier -> (reduce + RAdam + broadcast + clear) per flat buffer -> barrier, all on the current stream."""
+        dev = self.m.device
+        with ops._on(dev):
+            self._prepare()
+            self._epoch += 1
+            self._barrier(0)
+            for i, sp in enumerate(self._spans):
+                _lib_call("hn_dp_reduce_update", sp['g_tab'].data_ptr(), sp['g_mc'] or None, sp['p_tab'].data_ptr(),
+                          sp['p_mc'] or None, self.m[sp['off']:].data_ptr(), self.v[sp['off']:].data_ptr(), self.rank,
+                          self.world, sp['n'], self._hp_dev[i].data_ptr(), ops._stream())
+            self._barrier(1)
+        for sink in self._sinks:
+            sink.clean = True              # the kernel cleared every rank's gradient buffer
+        ops.param_epoch[0] += 1
+
+    @torch.no_grad()
+    def gather_moments(self):
+        """(exp_avg, exp_avg_sq) of the whole parameter buffer on every rank (for checkpoints): each rank contributes
+        the slices it owns."""
+        m, v = self.m.clone(), self.v.clone()
+        for sp in self._spans:
+            n, off = sp['n'], sp['off']
+            chunk = ((n + self.world - 1) // self.world + 3) & ~3
+            for t in (m, v):
+                for r in range(self.world):
+                    b, e = min(r * chunk, n), min(r * chunk + chunk, n)
+                    if e > b:
+                        dist.broadcast(t[off + b:off + e], src=r, group=self.group)
+        return m, v
+
+
+class SymmetricAllReduce:
+    """The summed all-reduce of one flat symmetric buffer through hn_dp_reduce_update(mode = -1): every rank reduces
+    its slice through the switch and multicasts the sum (bench.py's N > 1 step; NCCL stays the reference point)."""
+
+    def __init__(self, numel: int, device, group=None):
+        self.buf = SymmetricBuffer(numel, device, group)
+        self.signals = SymmetricBuffer(256, device, group, dtype=torch.int32)
+        self.rank, self.world = self.buf.rank, self.buf.world
+        self._g_tab, self._sig_tab = self.buf.ptr_table(0), self.signals.ptr_table(0)
+        self._hp = torch.tensor([0, 0, 0, 0, 0, 1.0, -1.0, 0], dtype=torch.float32, device=device)
+        self._epoch = 0
+        self.multicast = bool(self.buf.multicast_ptr)
+        dist.barrier(group=group)
+        torch.cuda.synchronize(device)
+
+    @property
+    def tensor(self) -> torch.Tensor:
+        return self.buf.tensor
+
+    def all_reduce(self):
+        self._epoch += 1
+        s = ops._stream()
+        _lib_call("hn_dp_barrier", self._sig_tab.data_ptr(), self.rank, self.world, 0, self._epoch, s)
+        _lib_call("hn_dp_reduce_update", self._g_tab.data_ptr(), self.buf.mc_ptr(0) or None, None, None, None, None,
+                  self.rank, self.world, self.buf.tensor.numel(), self._hp.data_ptr(), s)
+        _lib_call("hn_dp_barrier", self._sig_tab.data_ptr(), self.rank, self.world, 1, self._epoch, s)
+
+
+def _lib_call(name, *args):
+    from . import _lib
+    _lib.call(name, *args)
 
 
 class BucketedTableReducer:

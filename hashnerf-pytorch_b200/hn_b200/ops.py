@@ -251,6 +251,20 @@ class GradSink:
             self._views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
+    def adopt(self, flat: torch.Tensor) -> None:
+        """Use ``flat`` (zero-filled, one float per parameter element, e.g. a slice of a symmetric-memory buffer that
+        peers can read) as the gradient buffer from now on."""
+        if flat.numel() != sum(p.numel() for p in self.params) or flat.dtype != torch.float32:
+            raise RuntimeError("adopted gradient buffer has the wrong size or dtype")
+        self.flat = flat
+        GradSink._by_ptr[flat.data_ptr()] = weakref.ref(self)
+        self._views, off = [], 0
+        for p in self.params:
+            self._views.append(flat[off:off + p.numel()].view_as(p))
+            p.grad = self._views[-1]
+            off += p.numel()
+        self.clean = True
+
     def acquire(self) -> torch.Tensor:
         """Flat fp32 buffer to accumulate into; afterwards every param.grad is a slice of it."""
         fresh = False
@@ -490,6 +504,9 @@ class CompositeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, raw, z, rays_d, noise, white_bkgd):
+        # outputs the loss does not use (disp, acc, depth, ...) reach backward as None, not as zero tensors that a
+        # fill kernel each had to produce; hn_composite_bwd takes NULL for them
+        ctx.set_materialize_grads(False)
         dev = _need_cuda(raw, z, rays_d, noise)
         raw, z, rays_d = _f32c(raw), _f32c(z), _f32c(rays_d)
         noise = None if noise is None else _f32c(noise)
@@ -511,6 +528,8 @@ class CompositeFn(torch.autograd.Function):
         raw, z, rays_d, noise = ctx.saved_tensors
         R, S, white, has_noise = ctx.meta
         g = [None if t is None else _f32c(t) for t in (d_rgb, d_disp, d_acc, d_weights, d_depth, d_ent)]
+        if all(t is None for t in g):
+            return None, None, None, None, None
         d_raw = torch.empty_like(raw)
         with _on(raw.device):
             _lib.call("hn_composite_bwd", raw.data_ptr(), z.data_ptr(), rays_d.data_ptr(),

@@ -235,6 +235,26 @@ HN_API int hn_tv_loss_bwd_levels(const float* tables, const int64_t* origins, co
  * hp = {beta1, beta2, eps, weight_decay*lr, step_size*lr, grad_scale, mode, zero_grad}. */
 HN_API int hn_radam_step_dev(float* p, float* g, float* m, float* v, int64_t n, const float* hp, void* stream);
 
+/* ---- section 8e: the data-parallel exchange over peer memory ------------------------------------------------ */
+/* One rank per GPU.  All buffers are SYMMETRIC allocations (same size / layout on every rank) whose peer mappings
+ * the caller sets up (torch.distributed._symmetric_memory in hn_b200/dp.py); `*_ptrs_dev` are DEVICE arrays of the
+ * `world` peer pointers, `*_mc` multicast pointers to the same buffers (NVSwitch / NVLS) or NULL.
+ *
+ * hn_dp_barrier: every rank writes `epoch` into its flag of slot `slot` (0..3) in each peer's signal buffer
+ * (>= 256 uint32 per rank, zero-initialised; epochs must grow by one per use of a slot) and waits for all peers'
+ * flags; release / acquire at system scope.  A wait longer than ~2 s traps (a peer died) instead of hanging.
+ *
+ * hn_dp_reduce_update: over a span of n floats (multiple of 4; pointers 16-byte aligned) this rank takes slice
+ * rank of ceil(n / world) and, in one pass: sums the slice of every rank's gradient (multimem.ld_reduce when
+ * grad_mc != NULL, else one peer load per rank), applies the RAdam update of hn_radam_step_dev to ITS slice of
+ * (params, m, v) with hp = {beta1, beta2, eps, weight_decay*lr, step_size*lr, grad_scale, mode, -} read from device
+ * memory, stores the new parameters to every rank (multimem.st / peer stores) and clears the slice of every rank's
+ * gradient.  mode = -1: plain summed all-reduce in place of the gradient buffers, no optimizer (params, m, v unused).
+ * Bracket the calls of one exchange with two hn_dp_barrier calls (different slots). */
+HN_API int hn_dp_barrier(void* const* signal_ptrs_dev, int rank, int world, int slot, uint32_t epoch, void* stream);
+HN_API int hn_dp_reduce_update(void* const* grad_ptrs_dev, float* grad_mc, void* const* param_ptrs_dev, float* param_mc,
+                               float* m, float* v, int rank, int world, int64_t n, const float* hp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

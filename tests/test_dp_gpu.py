@@ -167,3 +167,95 @@ def test_dp_gradient_equivalence_two_gpus():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def _fused_worker(rank, world, port, q):
+    """FusedExchange (one pass over peer memory: reduce + RAdam on the owned slice + parameter multicast + gradient
+    clear) against GradSync.all_reduce + RAdam.step on the same batches; and SymmetricAllReduce against NCCL."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import cases
+        from hn_b200 import dp
+        from radam import RAdam
+        rays = torch.from_numpy(cases.rays(96, 7)).to(dev)
+        s, e = dp.shard_range(rays.shape[0], rank, world)
+
+        def make():
+            emb, nets, sh = _build(dev)
+            params = list(emb.parameters()) + [p for n in nets for p in n.parameters()]
+            dp.broadcast_parameters(params)
+            opt = RAdam([{"params": [p for n in nets for p in n.parameters()], "weight_decay": 1e-6},
+                         {"params": list(emb.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+            return emb, nets, sh, params, opt
+
+        # A: library all-reduce + the fused RAdam kernel
+        emb_a, nets_a, sh_a, params_a, opt_a = make()
+        sync = dp.GradSync(params_a)
+        opt_a.grad_scale = sync.grad_scale
+        # B: the fused exchange
+        emb_b, nets_b, sh_b, params_b, opt_b = make()
+        fx = dp.FusedExchange(opt_b, [emb_b] + nets_b)
+        steps = 7   # crosses RAdam's rectification switch (N_sma >= 5 from step 6 on)
+        for k in range(steps):
+            lr = 0.01 * (0.1 ** (k / 5.0))
+            for g in opt_a.param_groups + opt_b.param_groups:
+                g["lr"] = lr
+            batch = rays[s:e].contiguous() * (1.0 + 0.01 * k)
+            opt_a.zero_grad()
+            _loss_and_backward(emb_a, nets_a, sh_a, batch)
+            sync.all_reduce()
+            sync.wait()
+            opt_a.step()
+            opt_b.zero_grad()                      # what a run_nerf-style loop does; the buffers are already clear
+            _loss_and_backward(emb_b, nets_b, sh_b, batch)
+            fx.step()
+            torch.cuda.synchronize()
+            assert float(fx.grads_sym.tensor.abs().max()) == 0.0, "gradients must be cleared by the exchange"
+        flat_a = torch.cat([p.detach().reshape(-1) for p in params_a])
+        flat_b = torch.cat([p.detach().reshape(-1) for p in params_b])
+        err = float((flat_a - flat_b).abs().max()) / float(flat_a.abs().max())
+        assert err < 2e-6, f"fused exchange drifted from all-reduce + RAdam: {err}"   # summation order differs only
+        other = [torch.empty_like(flat_b) for _ in range(world)]
+        dist.all_gather(other, flat_b)
+        assert all(torch.equal(o, other[0]) for o in other), "ranks diverged under the fused exchange"
+        # sharded moments reassemble to what the unsharded optimizer holds
+        m, v = fx.gather_moments()
+        m_a = torch.cat([opt_a.state[p]["exp_avg"].reshape(-1) for p in list(emb_a.parameters())])
+        n_tab = m_a.numel()
+        assert float((m[:n_tab] - m_a).abs().max()) <= 2e-6 * float(m_a.abs().max()) + 1e-12
+        # plain all-reduce through the same kernel
+        sar = dp.SymmetricAllReduce(1 << 20, dev)
+        gen = torch.Generator(device=dev).manual_seed(5 + rank)
+        x = torch.randn(1 << 20, device=dev, generator=gen)
+        want = x.clone()
+        dist.all_reduce(want)
+        for _ in range(3):
+            sar.tensor.copy_(x)
+            sar.all_reduce()
+        torch.cuda.synchronize()
+        assert float((sar.tensor - want).abs().max()) <= 1e-6 * float(want.abs().max())
+        q.put((rank, f"ok multicast={fx.multicast}"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()[-2500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_exchange_two_gpus():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    print(results)
+    assert all(msg.startswith("ok") for _r, msg in results), results
