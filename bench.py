@@ -311,14 +311,14 @@ def workload_config(args, n_points):
                             "back is the 16 per-level gradient sums (64 B), not the 2.1 GB feature tensor",
             "parallelism": (f"dp{args.gpus} (points sharded; table gradient all-reduced "
                             + ("in 4 level buckets, each overlapping the next bucket's scatter" if args.bucket_overlap
-                               else "once after the scatter") + ")")
+                               else "once after the scatter") + f"; exchange: {getattr(args, 'exchange_used', args.exchange)})")
             if args.gpus > 1 else "single"}
 
 
 # ------------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------------
-def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, rank=0, world=1):
+def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, rank=0, world=1, fused_exchange=False):
     """BASELINE configs[2]/[3] shape: full coarse+fine render + loss + backward + RAdam on synthetic rays.
     With ``dist`` (N > 1): every rank renders its own n_rand rays, gradients are summed over ranks with one flat
     all-reduce per parameter group (hn_b200.dp.GradSync) and 1/world is applied inside the fused RAdam kernel;
@@ -367,8 +367,11 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, r
             step()
     else:
         from loss import total_variation_loss
-        sync = None
-        if dist is not None:
+        sync, fx = None, None
+        if dist is not None and fused_exchange:
+            from hn_b200.dp import FusedExchange
+            fx = FusedExchange(opt, [emb, coarse, fine])
+        elif dist is not None:
             from hn_b200.dp import GradSync
             sync = GradSync(list(emb.parameters()) + list(coarse.parameters()) + list(fine.parameters()))
 
@@ -380,6 +383,9 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, r
                                           emb.log2_hashmap_size, n_levels=emb.n_levels) for i in range(emb.n_levels))
             loss = loss + 1e-6 * tv
             loss.backward()
+            if fx is not None:      # collective + RAdam + zero_grad in one pass over peer memory
+                fx.step()
+                return
             if sync is not None:
                 sync.all_reduce()
                 sync.wait()
@@ -524,7 +530,21 @@ def run_ours(args):
     emb = HashEmbedder((lo.cpu(), hi.cpu()), log2_hashmap_size=log2T).to(dev)
     tables = emb.flat_tables()
     box, res = emb._geometry(dev)
-    dflat = torch.zeros(tables.numel(), device=dev)
+    # N > 1: the table gradient lives in symmetric memory and is summed by our own one-pass kernel (multimem
+    # reduce through the NVSwitch + multicast of the sum, csrc/dp_exchange.cu); --exchange nccl keeps the library call
+    sar, exchange = None, "none"
+    if dist is not None:
+        exchange = "nccl"
+        if args.exchange in ("auto", "nvls"):
+            try:
+                from hn_b200.dp import SymmetricAllReduce
+                sar = SymmetricAllReduce(tables.numel(), dev)
+                exchange = "hn_dp_reduce_update over symmetric memory (" + ("NVLS multimem" if sar.multicast else "peer loads/stores") + ")"
+            except Exception as exc:
+                if args.exchange == "nvls":
+                    raise
+                exchange = f"nccl (symmetric memory unavailable: {type(exc).__name__})"
+    dflat = sar.tensor if sar is not None else torch.zeros(tables.numel(), device=dev)
     out_holder = {}
 
     grid_res = ops.sort_grid_res(n)
@@ -555,7 +575,10 @@ def run_ours(args):
             bwd()
         elif reducer is None:
             bwd()
-            dist.all_reduce(dflat)
+            if sar is not None:
+                sar.all_reduce()
+            else:
+                dist.all_reduce(dflat)
         else:
             # level buckets: the all-reduce of bucket b runs on a side stream while bucket b+1 is scattered
             for b, e in buckets:
@@ -563,6 +586,7 @@ def run_ours(args):
                 reducer.reduce_levels(dflat, b, e)
             reducer.wait()
 
+    args.exchange_used = exchange
     dp_check = None
     if dist is not None:
         out_holder["xs4"] = ops.hash_sort_points(x, box, grid_res)
@@ -699,6 +723,17 @@ def run_ours(args):
         extra["train_ms_per_step_nrand8192_per_rank_dp"] = round(ms, 3)
         extra["train_step"] = ("data parallel: 8192 rays per rank, render_rays 64+128, mse+sparsity+16 TV terms, "
                                "backward, flat gradient all-reduce (GradSync), RAdam with 1/world folded in; eager")
+        if sar is not None:
+            try:
+                rps, ms = train_step_extra(dev, 8192, steps=10, warmup=3, dist=dist, rank=rank, world=world,
+                                           fused_exchange=True)
+                extra["train_rays_per_s_nrand8192_per_rank_dp_fused_exchange"] = round(rps, 1)
+                extra["train_ms_per_step_nrand8192_per_rank_dp_fused_exchange"] = round(ms, 3)
+                extra["train_step_fused_exchange"] = ("same step, but all-reduce + RAdam + zero_grad are ONE pass over "
+                                                      "peer memory (hn_b200.dp.FusedExchange: multimem reduce, sharded "
+                                                      "moments, parameter multicast)")
+            except Exception as exc:
+                extra["train_step_fused_exchange"] = f"failed: {type(exc).__name__}: {exc}"[:200]
         if args.dp_graph:
             rps, ms = train_step_extra(dev, 8192, steps=20, warmup=3, graphed=True, dist=dist, rank=rank, world=world)
             extra["train_rays_per_s_nrand8192_per_rank_dp_cuda_graph"] = round(rps, 1)
@@ -793,6 +828,9 @@ def main():
     ap.add_argument("--bucket-overlap", action="store_true",
                     help="N > 1: all-reduce the table gradient in 4 level buckets overlapped with the scatter instead "
                          "of once after it (measured slower: splitting the scatter costs more than the overlap hides)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "nccl"],
+                    help="N > 1: how gradients are exchanged -- our one-pass kernel over symmetric memory (auto: with "
+                         "fall-back to NCCL if symmetric memory cannot be set up) or the NCCL library all-reduce")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -137,17 +137,16 @@ class SymmetricBuffer:
     def __init__(self, numel: int, device, group=None, dtype=torch.float32):
         import torch.distributed._symmetric_memory as symm
         group = group if group is not None else dist.group.WORLD
-        try:  # torch < 2.8 wants the group announced first; newer versions do it in rendezvous
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass
         self.tensor = symm.empty(int(numel), dtype=dtype, device=device)
         self.tensor.zero_()
-        self.handle = symm.rendezvous(self.tensor, group=group)
+        try:
+            self.handle = symm.rendezvous(self.tensor, group=group)
+        except Exception:  # older torch wants the group announced first
+            symm.enable_symm_mem_for_group(group.group_name)
+            self.handle = symm.rendezvous(self.tensor, group=group)
         self.rank, self.world = int(self.handle.rank), int(self.handle.world_size)
         self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        mc = getattr(self.handle, "multicast_ptr", 0) or 0
-        self.multicast_ptr = int(mc) if getattr(self.handle, "has_multicast_support", lambda: bool(mc))() else 0
+        self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)   # 0: no NVSwitch multicast here
         self.itemsize = self.tensor.element_size()
 
     def ptr_table(self, offset_elems: int = 0) -> torch.Tensor:
