@@ -452,8 +452,8 @@ def dp_self_check(dist, dev, world, bwd, dflat, tables):
     got = float(red.double().sum().item())
     scale = float(red.double().abs().sum().item()) + 1e-30
     ok_sum = abs(got - expect) <= 1e-6 * scale
-    p = torch.nn.Parameter(tables.detach().clone())
-    p.grad = red
+    p = torch.nn.Parameter(tables.detach().reshape(-1).clone())
+    p.grad = red.reshape(-1)
     opt = RAdam([{"params": [p], "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
     opt.grad_scale = 1.0 / world
     opt.step()

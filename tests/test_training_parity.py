@@ -178,27 +178,17 @@ def test_graphed_step_matches_eager_step():
     assert trainer.graph is not None
     torch.cuda.synchronize()
     le, lg = torch.stack(losses_e).cpu().numpy(), torch.stack(losses_g).cpu().numpy()
-    # the capture step applies one extra (eager) update with the same batch, so compare up to the capture and the
-    # parameter trajectory by its loss curve afterwards
-    np.testing.assert_allclose(lg[:2], le[:2], rtol=1e-5)
+    # every batch is applied exactly once (2 eager warm-ups, the capture step's eager update, 9 replays): the loss
+    # curve follows the eager one step for step (atomics' summation order is the only difference)
+    np.testing.assert_allclose(lg[:3], le[:3], rtol=1e-5)
+    np.testing.assert_allclose(lg, le, rtol=2e-3)
     assert np.all(np.isfinite(lg)) and lg[-1] < lg[0]
 
-    # same schedule without the extra capture-time update: replay-only continuation equals eager continuation
-    opt_a, render_a, loss_a, params_a = build()
-    tr = GraphedTrainStep(n_rays, render_a, loss_a, opt_a, dev, warmup=2)
-    for k in range(3):                                   # 2 eager warm-ups + the capture step (eager + replay)
-        tr.step(all_rays[k], targets[k])
-    opt_b, render_b, loss_b, params_b = build()
-    start = torch.cat([p.detach().reshape(-1) for p in params_b]).clone()
-    seq = [0, 1, 2, 2] + list(range(3, n_steps))         # what the trainer has applied: step 2's batch twice
-    for k in seq:
-        opt_b.zero_grad()
-        loss = loss_b(render_b(all_rays[k]), targets[k])
-        loss.backward()
-        opt_b.step()
-    for k in range(3, n_steps):
-        tr.step(all_rays[k], targets[k])
-    torch.cuda.synchronize()
+    # and so does the parameter trajectory
+    opt_a, params_a = opt_g, params_g
+    opt_b, params_b = opt_e, params_e
+    _o, _r, _l, params_0 = build()
+    start = torch.cat([p.detach().reshape(-1) for p in params_0]).clone()
     # Adam's normalisation turns the atomics' summation-order noise into visible differences on a few rarely touched
     # table entries, so the runs are compared by the size of their difference against the size of the whole update:
     # a step applied with the next step's scalars (the first rectified step one step early) is > 10 % of it.
