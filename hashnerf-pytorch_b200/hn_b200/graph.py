@@ -89,9 +89,10 @@ class GraphedTrainStep:
             if self._warmup > 0:
                 self._warmup -= 1
                 self.loss = self._eager().detach()
-            else:
-                self.loss = self._capture()   # the eager step inside IS this call's optimisation step
-            return self.loss
+                return self.loss
+            # the eager step inside _capture() IS this call's optimisation step; from the next call on self.loss is
+            # the graph's static output, refreshed by every replay
+            return self._capture()
         self.opt.graph_prepare()
         self.graph.replay()
         ops.param_epoch[0] += 1
