@@ -318,7 +318,8 @@ def workload_config(args, n_points):
 # ------------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------------
-def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, rank=0, world=1, fused_exchange=False):
+def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, rank=0, world=1, fused_exchange=False,
+                     full_graph=False):
     """BASELINE configs[2]/[3] shape: full coarse+fine render + loss + backward + RAdam on synthetic rays.
     With ``dist`` (N > 1): every rank renders its own n_rand rays, gradients are summed over ranks with one flat
     all-reduce per parameter group (hn_b200.dp.GradSync) and 1/world is applied inside the fused RAdam kernel;
@@ -359,10 +360,37 @@ def train_step_extra(dev, n_rand, steps=8, warmup=3, graphed=False, dist=None, r
             sync = GradSync(list(emb.parameters()) + list(coarse.parameters()) + list(fine.parameters()))
             opt.grad_scale = sync.grad_scale
             grad_sync = sync.all_reduce_inline
-        trainer = GraphedTrainStep(n_rand, render_fn, loss_fn, opt, dev, warmup=2, grad_sync=grad_sync)
+        batcher, graph_loss = None, loss_fn
+        if full_graph:
+            # the COMPLETE step in the graph: batch construction (on-device pixel sampling + ray generation + target
+            # gather from resident images), render, mse + sparsity + the 16 TV terms, backward, RAdam + zero-grad
+            import loss as loss_mod
+            from hn_b200.batcher import DeviceRayBatcher
+            loss_mod.TV_FAST_DRAWS = True
+            H = W = 400
+            focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+            K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+            n_img = 8
+            images = torch.rand(n_img, H, W, 3, device=dev, generator=g)
+            poses = torch.zeros(n_img, 3, 4, device=dev)
+            for k in range(n_img):
+                a = 2 * np.pi * k / n_img
+                poses[k] = torch.tensor([[np.cos(a), 0, np.sin(a), 4 * np.sin(a)], [0, 1, 0, 0],
+                                         [-np.sin(a), 0, np.cos(a), 4 * np.cos(a)]], device=dev)
+            batcher = DeviceRayBatcher(images, poses, H, W, K, 2., 6., n_rand, dev, precrop_iters=0, seed=rank)
+
+            def graph_loss(ret, tgt):
+                tv = sum(loss_mod.total_variation_loss(emb.embeddings[i], emb.base_resolution, emb.finest_resolution, i,
+                                                       emb.log2_hashmap_size, n_levels=emb.n_levels)
+                         for i in range(emb.n_levels))
+                return loss_fn(ret, tgt) + 1e-6 * tv
+        trainer = GraphedTrainStep(n_rand, render_fn, graph_loss, opt, dev, warmup=2, grad_sync=grad_sync, batcher=batcher)
 
         def step():
-            trainer.step(rays, target)
+            if batcher is not None:
+                trainer.step()
+            else:
+                trainer.step(rays, target)
         for _ in range(4):  # eager warm-up + capture happen outside the timed region
             step()
     else:
@@ -780,6 +808,15 @@ def run_ours(args):
             rps, ms = train_step_extra(dev, n_rand, steps=20, graphed=True)
             extra[f"train_rays_per_s_nrand{n_rand}_cuda_graph"] = round(rps, 1)
             extra[f"train_ms_per_step_nrand{n_rand}_cuda_graph"] = round(ms, 3)
+            try:
+                rps, ms = train_step_extra(dev, n_rand, steps=20, graphed=True, full_graph=True)
+                extra[f"train_rays_per_s_nrand{n_rand}_cuda_graph_full"] = round(rps, 1)
+                extra[f"train_ms_per_step_nrand{n_rand}_cuda_graph_full"] = round(ms, 3)
+            except Exception as exc:
+                extra[f"train_nrand{n_rand}_cuda_graph_full"] = f"failed: {type(exc).__name__}: {exc}"[:200]
+            finally:
+                import loss as _loss_mod
+                _loss_mod.TV_FAST_DRAWS = False
         ms = inference_frame_extra(dev)
         extra["inference_800x800_ms_per_frame"] = round(ms, 2)
         extra["inference_800x800_mrays_per_s"] = round(0.64 / ms * 1e3, 2)
@@ -787,7 +824,9 @@ def run_ours(args):
         extra["reference_gpu"] = reference_gpu_extra(dev, log2T)
         extra["train_step"] = ("render_rays 64+128 samples/ray, perturb=1, white_bkgd, mse+sparsity, backward, RAdam"
                                "; eager = the drop-in API driven like run_nerf.py:608-642 incl. the 16 TV-loss terms, cuda_graph "
-                               "= hn_b200.graph.GraphedTrainStep replaying render+loss+backward+RAdam (no TV)")
+                               "= hn_b200.graph.GraphedTrainStep replaying render+loss+backward+RAdam(+zero-grad) on given rays (no TV); "
+                               "cuda_graph_full = the same graph with the on-device ray batcher (pixel sampling, ray "
+                               "generation, target gather from 8 resident 400x400 images) and the 16 TV terms inside")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -36,6 +36,11 @@ def _level_cube(min_resolution, max_resolution, level, n_levels):
 # requests, as long as they ask for increasing levels of the same unchanged tables, are served from that result.
 # Set to False to evaluate every request on its own (one launch per level, the previous behaviour).
 TV_SWEEP = True
+# False (default): a sweep draws its 16 cube origins with the reference's own 16 ``torch.randint`` calls, in order, so
+# a seeded run consumes the generator exactly as the reference does.  True: one ``torch.rand(L, 3)`` scaled to the
+# same integer ranges (same distribution, another stream): 3 launches instead of 17 -- for CUDA-graph steps, where
+# every node counts.
+TV_FAST_DRAWS = False
 
 
 class _Sweep:
@@ -58,12 +63,15 @@ def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, 
             raise RuntimeError("total_variation_loss: cube does not fit the level grid (random_(0, to<=0))")
         geo = ((key[:4], dev), spans,
                torch.tensor([c for _, c in res_cube], dtype=torch.int32, device=dev),
-               max(c for _, c in res_cube))
+               max(c for _, c in res_cube), torch.tensor(spans, dtype=torch.float32, device=dev)[:, None])
         _GEOMETRY[owner] = geo
-    _, spans, cubes, max_cube = geo
-    # the same draws, in the same order, as the reference's 16 consecutive calls make (loss.py:25): the generator
-    # stream -- and with it a seeded training run -- stays identical to the reference's
-    origins = torch.stack([torch.randint(0, sp, (3,), device=dev) for sp in spans])
+    _, spans, cubes, max_cube, span_t = geo
+    if TV_FAST_DRAWS:
+        origins = torch.minimum(torch.rand(len(spans), 3, device=dev) * span_t, span_t - 1).to(torch.int64)
+    else:
+        # the same draws, in the same order, as the reference's 16 consecutive calls make (loss.py:25): the generator
+        # stream -- and with it a seeded training run -- stays identical to the reference's
+        origins = torch.stack([torch.randint(0, sp, (3,), device=dev) for sp in spans])
     levels = owner._level_weights()
     sink = owner.grad_sink() if (torch.is_grad_enabled() and levels[0].requires_grad) else None
     return ops.TVSweepFn.apply(flat, origins, cubes, max_cube, int(log2_hashmap_size), int(flat.shape[-1]), sink,
