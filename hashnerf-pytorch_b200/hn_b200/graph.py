@@ -108,6 +108,10 @@ class GraphedTrainStep:
             eager_loss = self._eager().detach()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # nothing allocated by the eager steps may be released while the capture runs (a block freed inside a capture
+        # that other streams have used makes the allocator record events there: "dependency on uncaptured work")
+        for hook in ops.pre_capture_hooks:
+            hook()
         self.opt.graph_plan()
         self.opt.zero_grad(set_to_none=True)   # the captured backward must start with "no gradient yet"
         self.graph = torch.cuda.CUDAGraph()

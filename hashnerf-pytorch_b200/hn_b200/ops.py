@@ -63,6 +63,9 @@ def _stream() -> int:
 # bumped by every parameter update that goes through this package's raw-pointer kernels (RAdam.step, graph replay):
 # torch's own version counters do not see those writes, caches keyed on parameter values check this instead
 param_epoch = [0]
+# callables run right before a CUDA-graph capture starts (graph.GraphedTrainStep): modules that cache tensors between
+# calls drop them here, so that no cached block is released inside the capture
+pre_capture_hooks = []
 
 
 class _NoGuard:

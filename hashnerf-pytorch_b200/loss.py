@@ -49,6 +49,7 @@ class _Sweep:
 
 _SWEEPS = weakref.WeakKeyDictionary()    # HashEmbedder -> its current sweep (kept off the module: no pickling issues)
 _GEOMETRY = weakref.WeakKeyDictionary()  # HashEmbedder -> cached per-level cube sizes / spans on the device
+ops.pre_capture_hooks.append(_SWEEPS.clear)   # a cached sweep must not be released inside a graph capture
 
 
 def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels):
@@ -76,6 +77,15 @@ def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, 
     sink = owner.grad_sink() if (torch.is_grad_enabled() and levels[0].requires_grad) else None
     return ops.TVSweepFn.apply(flat, origins, cubes, max_cube, int(log2_hashmap_size), int(flat.shape[-1]), sink,
                                *levels)
+
+
+def total_variation_sweep(embed_fn):
+    """Opt-in: the TV terms of ALL levels of a HashEmbedder as one [L] tensor behind ONE autograd node -- what the
+    training loop's ``sum(total_variation_loss(embeddings[i], ...) for i in range(n_levels))`` (run_nerf.py:628-635)
+    adds up, without the 16 select / add nodes each way (CUDA-graph steps: every node costs a launch)."""
+    key = (embed_fn.base_resolution, embed_fn.finest_resolution, embed_fn.log2_hashmap_size, embed_fn.n_levels)
+    return _sweep_terms(embed_fn, key, embed_fn.base_resolution, embed_fn.finest_resolution,
+                        embed_fn.log2_hashmap_size, embed_fn.n_levels)
 
 
 def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2_hashmap_size, n_levels=16):

@@ -198,3 +198,59 @@ def test_graphed_step_matches_eager_step():
     assert update > 0 and diff <= 0.02 * update, f"graphed and eager runs drifted: |a-b| = {diff:.3e}, |update| = {update:.3e}"
     assert float((fa - fb).abs().max()) <= 5e-3 * float(fb.abs().max())
     assert [opt_a.state[p]['step'] for p in params_a] == [opt_b.state[p]['step'] for p in params_b]
+
+
+def test_full_graph_step_with_batcher_and_tv():
+    """The complete step as one CUDA graph: on-device batch construction (hn_sample_rays), render, mse + sparsity +
+    all TV terms (loss.total_variation_sweep, equal to the training loop's per-level sum), backward, RAdam with
+    zero-grad folded in.  Also covers ops.pre_capture_hooks: the TV sweep cached by the eager warm-up steps must not
+    be released inside the capture."""
+    import cases
+    import loss as loss_mod
+    from embedding.hash_encoding import HashEmbedder
+    from embedding.spherical_harmonic import SHEncoder
+    from hn_b200.batcher import DeviceRayBatcher
+    from hn_b200.graph import GraphedTrainStep
+    from models import NeRFSmall
+    from radam import RAdam
+    from run_nerf_helpers import render_rays, run_network, img2mse
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    emb = HashEmbedder((torch.tensor(cases.BBOX_UNIT[0]), torch.tensor(cases.BBOX_UNIT[1])), log2_hashmap_size=12).to(dev)
+    # the sweep helper == the loop's sum of per-level calls (same generator draws)
+    torch.manual_seed(9)
+    a = loss_mod.total_variation_sweep(emb).sum()
+    torch.manual_seed(9)
+    b = sum(loss_mod.total_variation_loss(emb.embeddings[i], emb.base_resolution, emb.finest_resolution, i,
+                                          emb.log2_hashmap_size, n_levels=emb.n_levels) for i in range(emb.n_levels))
+    np.testing.assert_allclose(float(a), float(b), rtol=1e-6)
+
+    mk = lambda: NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                           input_ch=32, input_ch_views=16).to(dev)
+    coarse, fine, sh = mk(), mk(), SHEncoder()
+    opt = RAdam([{"params": list(coarse.parameters()) + list(fine.parameters()), "weight_decay": 1e-6},
+                 {"params": list(emb.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    render_fn = lambda rb: render_rays(rb, coarse, qfn, 16, embed_fn=emb, retraw=True, perturb=1., N_importance=16,
+                                       network_fine=fine, white_bkgd=True)
+
+    def loss_fn(ret, tgt):
+        return img2mse(ret["rgb_map"], tgt) + img2mse(ret["rgb0"], tgt) \
+            + 1e-10 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum()) \
+            + 1e-6 * loss_mod.total_variation_sweep(emb).sum()
+
+    H, W, n_img, n_rays = 24, 32, 3, 128
+    focal = 30.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    rs = np.random.RandomState(1)
+    images = rs.rand(n_img, H, W, 3).astype(np.float32)
+    poses = np.tile(np.array([[1, 0, 0, 0.0], [0, 1, 0, 0.0], [0, 0, 1, 1.2]], np.float32), (n_img, 1, 1))
+    batcher = DeviceRayBatcher(images, poses, H, W, K, 0.5, 2.5, n_rays, dev, seed=2)
+    trainer = GraphedTrainStep(n_rays, render_fn, loss_fn, opt, dev, warmup=2, batcher=batcher)
+    start = emb.flat_tables().clone()
+    losses = [float(trainer.step()) for _ in range(8)]
+    assert trainer.graph is not None and np.all(np.isfinite(losses))
+    assert opt.fused_zero_grad and float(emb.grad_sink().flat.abs().max()) == 0.0
+    assert not torch.equal(emb.flat_tables(), start)
+    assert len(set(round(l, 9) for l in losses)) > 4, "every replay must see a fresh batch"
+    assert [opt.state[p]['step'] for p in emb.parameters()] == [8] * 16

@@ -19,4 +19,9 @@ fi
 if python tools/prof_hash.py > $OUT/plain_hash_$TAG.log 2>&1; then
   ncu --set full --clock-control none --import-source on -k regex:"hash_fwd|hash_bwd|sort" -c 12 -o $OUT/prof_hash_$TAG -f python tools/prof_hash.py > $OUT/ncu_hash_$TAG.log 2>&1
 fi
+if python tools/prof_mlp.py > $OUT/plain_mlp_$TAG.log 2>&1; then
+  ncu --set full --clock-control none --import-source on -k regex:"mlp_tc" -s 3 -c 3 -o $OUT/prof_mlp_$TAG -f python tools/prof_mlp.py > $OUT/ncu_mlp_$TAG.log 2>&1
+fi
+python tools/measure_tensor_peak.py > $OUT/tensor_peaks_$TAG.json 2>&1
+python tools/time_mlp.py > $OUT/time_mlp_$TAG.log 2>&1
 ls -la $OUT | tail -20
