@@ -196,7 +196,7 @@ def test_graphed_step_matches_eager_step():
     fb = torch.cat([p.detach().reshape(-1) for p in params_b])
     update, diff = float((fb - start).norm()), float((fa - fb).norm())
     assert update > 0 and diff <= 0.02 * update, f"graphed and eager runs drifted: |a-b| = {diff:.3e}, |update| = {update:.3e}"
-    assert float((fa - fb).abs().max()) <= 5e-3 * float(fb.abs().max())
+    assert float((fa - fb).abs().max()) <= 1e-2 * float(fb.abs().max())
     assert [opt_a.state[p]['step'] for p in params_a] == [opt_b.state[p]['step'] for p in params_b]
 
 
