@@ -108,8 +108,11 @@ class GraphedTrainStep:
             eager_loss = self._eager().detach()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        # nothing allocated by the eager steps may be released while the capture runs (a block freed inside a capture
-        # that other streams have used makes the allocator record events there: "dependency on uncaptured work")
+        # No autograd graph over the parameters may be alive when the capture starts: a leaf's AccumulateGrad node
+        # belongs to the stream it was created on and lives as long as any graph references it, so a graph kept from
+        # an eager step (e.g. the TV sweep loss.py caches between calls) would make the captured backward synchronise
+        # with that uncaptured stream -- cudaErrorStreamCaptureIsolation.  Modules that cache such tensors register a
+        # hook that drops them; callers must not hold on to losses of earlier steps either (detach them).
         for hook in ops.pre_capture_hooks:
             hook()
         self.opt.graph_plan()

@@ -63,8 +63,8 @@ def _stream() -> int:
 # bumped by every parameter update that goes through this package's raw-pointer kernels (RAdam.step, graph replay):
 # torch's own version counters do not see those writes, caches keyed on parameter values check this instead
 param_epoch = [0]
-# callables run right before a CUDA-graph capture starts (graph.GraphedTrainStep): modules that cache tensors between
-# calls drop them here, so that no cached block is released inside the capture
+# callables run right before a CUDA-graph capture starts (graph.GraphedTrainStep): modules that cache tensors carrying
+# an autograd graph between calls drop them here (see GraphedTrainStep._capture)
 pre_capture_hooks = []
 
 

@@ -49,7 +49,7 @@ class _Sweep:
 
 _SWEEPS = weakref.WeakKeyDictionary()    # HashEmbedder -> its current sweep (kept off the module: no pickling issues)
 _GEOMETRY = weakref.WeakKeyDictionary()  # HashEmbedder -> cached per-level cube sizes / spans on the device
-ops.pre_capture_hooks.append(_SWEEPS.clear)   # a cached sweep must not be released inside a graph capture
+ops.pre_capture_hooks.append(_SWEEPS.clear)   # a cached sweep keeps an autograd graph alive across a graph capture
 
 
 def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels):

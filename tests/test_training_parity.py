@@ -224,6 +224,7 @@ def test_full_graph_step_with_batcher_and_tv():
     b = sum(loss_mod.total_variation_loss(emb.embeddings[i], emb.base_resolution, emb.finest_resolution, i,
                                           emb.log2_hashmap_size, n_levels=emb.n_levels) for i in range(emb.n_levels))
     np.testing.assert_allclose(float(a), float(b), rtol=1e-6)
+    del a, b   # no autograd graph over the parameters may be alive when the capture starts (see GraphedTrainStep)
 
     mk = lambda: NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
                            input_ch=32, input_ch_views=16).to(dev)
