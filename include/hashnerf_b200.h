@@ -54,7 +54,8 @@ HN_API int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   "mlp_dw_nbuf"                    weight-gradient kernel: 1 = two CTAs/SM, one staging buffer (default); 2 = one
  *                                    CTA/SM, two buffers
  *   "mlp_fwd_one_cta", "mlp_dw_ablate"   profiling only (occupancy / phase ablations; the latter breaks results)
- * Unknown keys return HN_EINVAL. */
+ * Unknown keys return HN_EINVAL.  The knobs are PROCESS-GLOBAL and unsynchronised: set them before the threads that
+ * launch kernels start (they exist for sweeps and A/B runs, not for per-call configuration). */
 HN_API int hn_set_tuning(const char* key, int value);
 
 /* ---- (a3) spatial hash : embedding/hash_encoding.py:112-128 ------------------------------------ */
@@ -70,9 +71,11 @@ HN_API int hn_voxel_vertices(const float* x, const float* bbox, const float* res
                       int log2T, int64_t* hashed, float* vmin, float* vmax, void* stream);
 
 /* ---- (a4-a6) multiresolution hash encoding : embedding/hash_encoding.py:84-110, 130-163 -------- */
-/* tables: [L, 2^log2T, F] f32 (level l's nn.Embedding.weight is the l-th slab).  F == 2.
+/* tables: [L, 2^log2T, F] f32 (level l's nn.Embedding.weight is the l-th slab).  F in {1, 2, 4}.
  * out: [N, L*F] f32, level-major features.  keep: [N] uint8, the mask forward() returns
- * (last level's in-box test on the already-clamped coordinates; may be NULL). */
+ * (last level's in-box test on the already-clamped coordinates; may be NULL).
+ * tables, out (and dy, dtables, xs4 of the calls below) must be 16-byte aligned: the kernels use vector accesses;
+ * a violation returns HN_EINVAL instead of faulting.  N * ceil(L / levels-per-thread) must fit a 1-D grid (2^31-1). */
 HN_API int hn_hash_encode_fwd(const float* x, const float* tables, const float* bbox, const float* resolutions,
                        int64_t N, int L, int F, int log2T, float* out, uint8_t* keep, void* stream);
 /* Autograd of the above w.r.t. the tables: dtables[l, h_c, :] += dy[p, l*F:(l+1)*F] * W_c(p) for the 8

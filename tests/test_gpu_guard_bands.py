@@ -123,3 +123,33 @@ def test_render_stage_guard_bands(R, S, Ni):
     torch.cuda.synchronize()
     for k, gd in outs.items():
         gd.check(k)
+
+
+def test_hash_entry_points_reject_misaligned_pointers_and_huge_resolutions():
+    """the vector paths need 16-byte aligned tables / out / dy / dtables -- a misaligned pointer must come
+    back as HN_EINVAL (RuntimeError in the shim), not as a sticky misaligned-address fault; and level resolutions of
+    2^21 and more must not alias voxels in the warp-aggregation key (such lanes scatter on their own)."""
+    from hn_b200 import _lib, ops
+    box, res = _geom()
+    n = 64
+    x = torch.rand(n, 3, device=DEV) * 3 - 1.5
+    tables = torch.zeros(16 * 1024 * 2 + 4, device=DEV)
+    out = torch.empty(n * 32 + 4, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        _lib.call("hn_hash_encode_fwd", x.data_ptr(), tables.data_ptr() + 4, box.data_ptr(), res.data_ptr(), n, 16, 2, 10,
+                  out.data_ptr(), None, s)
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        _lib.call("hn_hash_encode_bwd_ordered", x.data_ptr(), out.data_ptr() + 8, box.data_ptr(), res.data_ptr(), n, 16, 2,
+                  10, tables.data_ptr(), s)
+    torch.cuda.synchronize()   # the context is intact
+    # resolutions >= 2^21: ordered (aggregating) scatter == plain scatter
+    big = torch.full((2,), float(1 << 22), device=DEV)
+    box1 = torch.tensor([0., 0., 0., 1., 1., 1.], device=DEV)
+    pts = (torch.rand(4096, 1, device=DEV) * torch.ones(1, 3, device=DEV)).contiguous()   # along the diagonal: huge indices
+    dy = torch.randn(4096, 4, device=DEV)
+    g_plain = torch.zeros(2 * 4096 * 2, device=DEV)
+    g_agg = torch.zeros_like(g_plain)
+    ops.hash_encode_backward(pts, dy, box1, big, 2, 2, 12, g_plain, ordered=False)
+    ops.hash_encode_backward(pts, dy, box1, big, 2, 2, 12, g_agg, ordered=True)
+    assert float((g_plain - g_agg).abs().max()) <= 1e-4 * float(g_plain.abs().max())

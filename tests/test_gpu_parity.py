@@ -299,9 +299,10 @@ def test_hash_encode_other_feature_widths(F, L):
     assert (got - an).abs().max().item() <= GRAD_RTOL * an.abs().max().item()
 
 
-def test_hash_encode_full_size_properties():
-    """BASELINE config 2 size (2^24 points, T=19): properties that need no full-size oracle."""
-    n, log2T = 1 << 24, 19
+@pytest.mark.parametrize("log2T", [19, 14, 22])
+def test_hash_encode_full_size_properties(log2T):
+    """BASELINE config 2 sizes (2^24 points, T in {14, 19, 22}): properties that need no full-size oracle."""
+    n = 1 << 24
     emb, tables = make_embedder(cases.BBOX_UNIT, log2T)
     assert emb.coherent is None  # default policy: this many points take the sorted (coherent) path
     gen = torch.Generator(device=DEV).manual_seed(0)
