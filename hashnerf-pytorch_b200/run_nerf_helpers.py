@@ -64,7 +64,7 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     flat = inputs.reshape(-1, inputs.shape[-1])
     per_ray = inputs.shape[-2] if inputs.dim() >= 3 else 1
 
-    if isinstance(fn, NeRFSmall) and isinstance(embed_fn, HashEmbedder) and viewdirs is not None \
+    if isinstance(fn, NeRFSmall) and fn.fused and isinstance(embed_fn, HashEmbedder) and viewdirs is not None \
             and isinstance(embeddirs_fn, SHEncoder) and embeddirs_fn.degree == 4 \
             and viewdirs.shape[0] * per_ray == flat.shape[0]:
         embedded, keep_u8 = embed_fn.encode(flat, ordered=inputs.dim() >= 3)  # [R,S,3]: samples along rays

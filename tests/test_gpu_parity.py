@@ -431,6 +431,32 @@ def test_mlp_fused_backward_matches_two_kernel_backward(n, per_ray):
     assert float(((dw1 - dw0).abs() / (dw0.abs() + 1e-2 * dw0.abs().max())).max()) < 1e-3
 
 
+def test_nerfsmall_default_geometry_matches_reference_forward():
+    """NeRFSmall() with the constructor's OWN defaults (models.py:97-104: 3 sigma layers, 4 colour layers, input_ch 3)
+    -- a geometry the fused kernels do not cover -- keeps the reference's behaviour through the layer-by-layer CUDA
+    path: parameter names / shapes and outputs equal the layer arithmetic of models.py:151-174."""
+    from models import NeRFSmall
+    torch.manual_seed(2)
+    net = NeRFSmall().to(DEV)
+    assert not net.fused
+    assert [tuple(l.weight.shape) for l in net.sigma_net] == [(64, 3), (64, 64), (16, 64)]
+    assert [tuple(l.weight.shape) for l in net.color_net] == [(64, 18), (64, 64), (64, 64), (3, 64)]
+    x = torch.randn(100, 6, device=DEV, requires_grad=True)
+    out = net(x)
+    w = [l.weight.detach().cpu().double() for l in list(net.sigma_net) + list(net.color_net)]
+    xd = x.detach().cpu().double()
+    h = torch.relu(torch.relu(xd[:, :3] @ w[0].T) @ w[1].T) @ w[2].T
+    sigma, geo = h[:, 0], h[:, 1:]
+    c = torch.cat([xd[:, 3:], geo], -1)
+    c = torch.relu(torch.relu(torch.relu(c @ w[3].T) @ w[4].T) @ w[5].T) @ w[6].T
+    want = torch.cat([c, sigma[:, None]], -1)
+    close(out, want.float(), 1e-4, atol=1e-5)
+    out.sum().backward()
+    assert x.grad is not None and net.sigma_net[0].weight.grad is not None
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        NeRFSmall()(torch.randn(4, 6))
+
+
 def test_mlp_weight_kernel_variants_agree():
     """The two launch shapes of the weight-gradient kernel (mlp_dw_nbuf: two CTAs/SM with one staging buffer, one
     CTA/SM with two) must produce the same gradients, on a batch large enough to keep every CTA busy for a few tiles."""
@@ -1098,5 +1124,5 @@ def test_error_behaviour():
     with pytest.raises(RuntimeError):
         _lib.set_tuning("no_such_knob", 1)
     with pytest.raises(NotImplementedError):
-        from models import NeRFSmall
-        NeRFSmall()  # the reference's never-used default geometry
+        from models import NeRF
+        NeRF()  # the positional-encoding network of the dead i_embed = 0 branch
