@@ -90,7 +90,9 @@ class HashEmbedder(nn.Module):
         # True / False force the choice.
         self.coherent = None
         # True: backward accumulates in place into one persistent flat gradient buffer and points
-        # embeddings[l].weight.grad at its slices (see ops.GradSink); False: plain autograd gradients.
+        # embeddings[l].weight.grad at its slices (see ops.GradSink) -- what loss.backward() + optimizer.step() see is
+        # identical to autograd's, but the autograd node itself returns no parameter gradient, so
+        # torch.autograd.grad(loss, params), parameter hooks and DDP need False: plain autograd gradients.
         self.fused_grad_accumulation = True
         self._sink = None
 

@@ -334,6 +334,11 @@ class HashEncodeFn(torch.autograd.Function):
     def backward(ctx, dout, _dkeep):
         x, bbox6, resolutions = ctx.saved_tensors
         L, F, log2T, use_sort, ordered = ctx.meta
+        if ctx.needs_input_grad[0]:
+            # the reference is differentiable w.r.t. the points (through the interpolation weights); nothing on the
+            # training path asks for that gradient and no kernel computes it -- say so instead of returning None
+            raise RuntimeError("hashnerf_b200: the gradient of the hash encoding w.r.t. the input points is not "
+                               "implemented (detach the points, or use the reference's encoder for that term)")
         T = 1 << log2T
         sink = ctx.sink
         dflat = sink.acquire() if sink is not None else torch.zeros(L * T * F, dtype=torch.float32, device=x.device)
