@@ -466,6 +466,33 @@ def inference_frame_extra(dev, H=800, W=800, dist=None):
     return ms
 
 
+def fern_frame_extra(dev):
+    """The LLFF half of BASELINE configs[4]: fern.txt shapes -- a 378 x 504 frame (factor 8), N_samples 64 +
+    N_importance 64, forward-facing NDC rays (near 0, far 1, hn_ndc_rays), raw_noise_std 0 at test time, no white
+    background (configs/fern.txt:9-14; run_nerf.py:246-247)."""
+    from embedding.hash_encoding import HashEmbedder
+    from embedding.spherical_harmonic import SHEncoder
+    from models import NeRFSmall
+    from run_nerf_helpers import render, run_network
+    torch.manual_seed(0)
+    H, W, focal = 378, 504, 407.6
+    box = (torch.tensor([-1.6, -1.6, -1.1]), torch.tensor([1.6, 1.6, 1.1]))   # the bbox.py rule for NDC scenes: +-(1 + margin)
+    emb = HashEmbedder(box, log2_hashmap_size=19).to(dev)
+    mk = lambda: NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                           input_ch=32, input_ch_views=16).to(dev)
+    coarse, fine, sh = mk(), mk(), SHEncoder()
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = torch.tensor([[1, 0, 0, 0.05], [0, 1, 0, -0.02], [0, 0, 1, 0.3]], device=dev)
+    kw = dict(ndc=True, near=0., far=1., use_viewdirs=True, network_fn=coarse, network_fine=fine, network_query_fn=qfn,
+              N_samples=64, N_importance=64, embed_fn=emb, perturb=0., raw_noise_std=0., white_bkgd=False)
+
+    def frame():
+        with torch.no_grad():
+            render(H, W, K, chunk=1024 * 32, c2w=c2w, **kw)
+    return time_loop(frame, 3, 1) / 3
+
+
 def dp_self_check(dist, dev, world, bwd, dflat, tables):
     """N > 1, once before timing: (1) the all-reduced table gradient's checksum equals the sum of the per-rank
     checksums gathered separately; (2) after one fused RAdam step on the reduced gradient (1/world folded in) the
@@ -813,6 +840,9 @@ def run_ours(args):
         ms = inference_frame_extra(dev)
         extra["inference_800x800_ms_per_frame"] = round(ms, 2)
         extra["inference_800x800_mrays_per_s"] = round(0.64 / ms * 1e3, 2)
+        ms = fern_frame_extra(dev)
+        extra["inference_fern_378x504_ndc_64p64_ms_per_frame"] = round(ms, 2)
+        extra["inference_fern_378x504_ndc_64p64_mrays_per_s"] = round(378 * 504 / ms / 1e3, 2)
         torch.cuda.empty_cache()
         extra["reference_gpu"] = reference_gpu_extra(dev, log2T)
         for n_rand in (1024, 8192):   # last: a failed capture must not be able to disturb the other legs

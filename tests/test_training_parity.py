@@ -255,3 +255,92 @@ def test_full_graph_step_with_batcher_and_tv():
     assert not torch.equal(emb.flat_tables(), start)
     assert len(set(round(l, 9) for l in losses)) > 4, "every replay must see a fresh batch"
     assert [opt.state[p]['step'] for p in emb.parameters()] == [8] * 16
+
+
+def test_psnr_parity_against_the_reference_on_the_same_gpu():
+    """The north star's PSNR criterion at the reference's OWN hyper-parameters and with the reference's OWN code as
+    the comparison: chair.txt geometry (L=16, F=2, T=2^19, finest 512, 64 + 128 samples, N_rand 1024, RAdam lr 0.01,
+    sparsity 1e-10, TV 1e-6 on all 16 levels), the unmodified reference modules (oracle/_ref through ref_loader) on
+    device='cuda' of this GPU against this package's modules: identical initial parameters, identical ray batches,
+    deterministic sampling, identical TV cubes (generator re-seeded per step).  Held-out PSNR, averaged over the last
+    five evaluations, must agree within 0.1 dB."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not available (oracle/make_ref.py not run)")
+    from embedding.hash_encoding import HashEmbedder
+    from embedding.spherical_harmonic import SHEncoder
+    from loss import total_variation_loss
+    from models import NeRFSmall
+    from radam import RAdam
+    from run_nerf_helpers import render_rays, run_network, img2mse
+
+    log2T, s_c, s_f, n_rand, steps, lr = 19, 64, 128, 1024, 200, 0.01
+    evals_at = (steps - 40, steps - 30, steps - 20, steps - 10, steps)
+    batches = [scene_rays(n_rand, 500 + i) for i in range(steps)]
+    test_rays, test_rgb = scene_rays(2048, 4242)
+    geo = dict(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64, input_ch=32,
+               input_ch_views=16)
+    box = (torch.tensor(BBOX[0]), torch.tensor(BBOX[1]))
+
+    def train(mods, render, tv_loss, opt):
+        emb, coarse, fine, sh, qfn = mods
+        kw = dict(N_samples=s_c, embed_fn=emb, retraw=True, perturb=0., N_importance=s_f, network_fine=fine,
+                  white_bkgd=True, raw_noise_std=0.)
+        evals, first = [], None
+        for step, (rays, rgb) in enumerate(batches, start=1):
+            ret = render(t(rays).to(DEV), coarse, qfn, **kw)
+            opt.zero_grad()
+            tgt = t(rgb).to(DEV)
+            loss = img2mse(ret["rgb_map"], tgt) + img2mse(ret["rgb0"], tgt) \
+                + 1e-10 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum())
+            torch.manual_seed(step)   # the same TV cubes in both runs
+            tv = sum(tv_loss(emb.embeddings[i], 16, 512, i, log2T, n_levels=16) for i in range(16))
+            loss = loss + 1e-6 * tv
+            loss.backward()
+            opt.step()
+            new_lr = lr * (0.1 ** (step / 10000.0))
+            for g in opt.param_groups:
+                g["lr"] = new_lr
+            first = loss.item() if first is None else first
+            if step in evals_at:
+                with torch.no_grad():
+                    out = render(t(test_rays).to(DEV), coarse, qfn, **kw)
+                evals.append(psnr(out["rgb_map"].cpu().numpy(), test_rgb))
+        return float(np.mean(evals)), first
+
+    # ---- the reference's own modules on this GPU (they rely on the CUDA default tensor type, run_nerf.py:725)
+    torch.set_default_tensor_type('torch.cuda.FloatTensor')
+    try:
+        ref = ref_loader.load("cuda")
+        torch.manual_seed(123)
+        r_emb = ref.HashEmbedder((box[0].to(DEV), box[1].to(DEV)), log2_hashmap_size=log2T).to(DEV)
+        r_coarse, r_fine, r_sh = ref.NeRFSmall(**geo).to(DEV), ref.NeRFSmall(**geo).to(DEV), ref.SHEncoder()
+        init = {"emb": {k: v.detach().clone() for k, v in r_emb.state_dict().items()},
+                "coarse": {k: v.detach().clone() for k, v in r_coarse.state_dict().items()},
+                "fine": {k: v.detach().clone() for k, v in r_fine.state_dict().items()}}
+        r_opt = ref.RAdam([{"params": list(r_coarse.parameters()) + list(r_fine.parameters()), "weight_decay": 1e-6},
+                           {"params": list(r_emb.parameters()), "eps": 1e-15}], lr=lr, betas=(0.9, 0.99))
+        r_q = lambda i, v, fn: ref.run_network(i, v, fn, embed_fn=r_emb, embeddirs_fn=r_sh, netchunk=1 << 16)
+        psnr_ref, first_ref = train((r_emb, r_coarse, r_fine, r_sh, r_q), ref.render_rays, ref.total_variation_loss, r_opt)
+    finally:
+        torch.set_default_tensor_type('torch.FloatTensor')
+
+    # ---- this package, from the same initial parameters
+    emb = HashEmbedder(box, log2_hashmap_size=log2T).to(DEV)
+    coarse, fine, sh = NeRFSmall(**geo).to(DEV), NeRFSmall(**geo).to(DEV), SHEncoder()
+    emb.load_state_dict(init["emb"])
+    coarse.load_state_dict(init["coarse"])
+    fine.load_state_dict(init["fine"])
+    opt = RAdam([{"params": list(coarse.parameters()) + list(fine.parameters()), "weight_decay": 1e-6},
+                 {"params": list(emb.parameters()), "eps": 1e-15}], lr=lr, betas=(0.9, 0.99), fused_zero_grad=True)
+    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    psnr_ours, first_ours = train((emb, coarse, fine, sh, qfn), render_rays, total_variation_loss, opt)
+
+    print(f"PSNR (mean of steps {evals_at}): ours {psnr_ours:.3f} dB, reference on the same GPU {psnr_ref:.3f} dB; "
+          f"first loss {first_ours:.6f} / {first_ref:.6f}")
+    assert abs(first_ours - first_ref) <= 2e-5 * abs(first_ref)
+    assert psnr_ref > 15.0, "the synthetic scene should be learnable in this many steps"
+    assert abs(psnr_ours - psnr_ref) <= 0.1
