@@ -35,6 +35,15 @@ def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def slice_bounds(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """[begin, end) of the slice of an n-float flat buffer that ``rank`` owns in hn_dp_reduce_update: chunks of
+    ceil(n / world) rounded up to 4 floats (16-byte vectors), the last ranks possibly empty.  Mirrors
+    csrc/dp_exchange.cu."""
+    chunk = ((n + world_size - 1) // world_size + 3) & ~3
+    begin = min(rank * chunk, n)
+    return begin, min(begin + chunk, n)
+
+
 def _flat_runs(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     """Group tensors that sit back to back in one storage into single flat views (zero copy)."""
     runs, cur = [], []
@@ -281,10 +290,9 @@ class FusedExchange:
         m, v = self.m.clone(), self.v.clone()
         for sp in self._spans:
             n, off = sp['n'], sp['off']
-            chunk = ((n + self.world - 1) // self.world + 3) & ~3
             for t in (m, v):
                 for r in range(self.world):
-                    b, e = min(r * chunk, n), min(r * chunk + chunk, n)
+                    b, e = slice_bounds(n, r, self.world)
                     if e > b:
                         dist.broadcast(t[off + b:off + e], src=r, group=self.group)
         return m, v

@@ -106,3 +106,17 @@ def test_shard_range_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - s for s, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_exchange_slices_tile_the_buffer():
+    """hn_dp_reduce_update's ownership rule (dp.slice_bounds mirrors csrc/dp_exchange.cu): for every buffer length and
+    world size the slices are disjoint, 16-byte aligned and cover [0, n) exactly."""
+    from hn_b200 import dp
+    for n in (4, 8, 9344, 16 * (1 << 19) * 2, 1000 * 4, 12):
+        for world in (1, 2, 3, 4, 7, 8, 64):
+            cursor = 0
+            for r in range(world):
+                b, e = dp.slice_bounds(n, r, world)
+                assert b == cursor and b % 4 == 0 and e >= b
+                cursor = e
+            assert cursor == n
