@@ -262,8 +262,11 @@ def test_psnr_parity_against_the_reference_on_the_same_gpu():
     the comparison: chair.txt geometry (L=16, F=2, T=2^19, finest 512, 64 + 128 samples, N_rand 1024, RAdam lr 0.01,
     sparsity 1e-10, TV 1e-6 on all 16 levels), the unmodified reference modules (oracle/_ref through ref_loader) on
     device='cuda' of this GPU against this package's modules: identical initial parameters, identical ray batches,
-    deterministic sampling, identical TV cubes (generator re-seeded per step).  Held-out PSNR, averaged over the last
-    five evaluations, must agree within 0.1 dB."""
+    deterministic sampling, identical TV cubes (generator re-seeded per step).  Held-out PSNR must agree within
+    0.1 dB.  The reference is bit-reproducible run to run on this GPU; this package's scatter uses atomics, and training
+    amplifies their summation-order noise chaotically: single evaluations of two of OUR runs differ by up to 0.3 dB
+    while PSNR still climbs 0.05 dB per step (tools/exp_psnr_spread.py), so the comparison averages 20 evaluations
+    over the last 100 steps on 4096 held-out rays (observed |difference| of the means: 0.01-0.04 dB)."""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
@@ -277,10 +280,10 @@ def test_psnr_parity_against_the_reference_on_the_same_gpu():
     from radam import RAdam
     from run_nerf_helpers import render_rays, run_network, img2mse
 
-    log2T, s_c, s_f, n_rand, steps, lr = 19, 64, 128, 1024, 200, 0.01
-    evals_at = (steps - 40, steps - 30, steps - 20, steps - 10, steps)
+    log2T, s_c, s_f, n_rand, steps, lr = 19, 64, 128, 1024, 240, 0.01
+    evals_at = tuple(range(steps - 95, steps + 1, 5))
     batches = [scene_rays(n_rand, 500 + i) for i in range(steps)]
-    test_rays, test_rgb = scene_rays(2048, 4242)
+    test_rays, test_rgb = scene_rays(4096, 4242)
     geo = dict(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64, input_ch=32,
                input_ch_views=16)
     box = (torch.tensor(BBOX[0]), torch.tensor(BBOX[1]))
@@ -339,7 +342,8 @@ def test_psnr_parity_against_the_reference_on_the_same_gpu():
     qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
     psnr_ours, first_ours = train((emb, coarse, fine, sh, qfn), render_rays, total_variation_loss, opt)
 
-    print(f"PSNR (mean of steps {evals_at}): ours {psnr_ours:.3f} dB, reference on the same GPU {psnr_ref:.3f} dB; "
+    print(f"PSNR (mean of {len(evals_at)} evaluations, steps {evals_at[0]}..{evals_at[-1]}): ours {psnr_ours:.3f} dB, "
+          f"reference on the same GPU {psnr_ref:.3f} dB; "
           f"first loss {first_ours:.6f} / {first_ref:.6f}")
     assert abs(first_ours - first_ref) <= 2e-5 * abs(first_ref)
     assert psnr_ref > 15.0, "the synthetic scene should be learnable in this many steps"

@@ -1,0 +1,71 @@
+"""Run-to-run spread of the held-out PSNR of the reference itself (its CUDA embedding backward uses atomics) and of
+this package, same data and initial parameters: how much of a PSNR difference is trajectory chaos?"""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in ("tests", "oracle", "hashnerf-pytorch_b200"):
+    sys.path.insert(0, os.path.join(ROOT, p))
+import test_training_parity as T
+import ref_loader
+from embedding.hash_encoding import HashEmbedder
+from embedding.spherical_harmonic import SHEncoder
+from loss import total_variation_loss
+from models import NeRFSmall
+from radam import RAdam
+from run_nerf_helpers import render_rays, run_network, img2mse
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+DEV = "cuda"
+log2T, s_c, s_f, n_rand, steps, lr = 19, 64, 128, 1024, int(os.environ.get("STEPS", 200)), 0.01
+evals_at = tuple(range(steps - 45, steps + 1, 5))
+batches = [T.scene_rays(n_rand, 500 + i) for i in range(steps)]
+test_rays, test_rgb = T.scene_rays(4096, 4242)
+geo = dict(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64, input_ch=32, input_ch_views=16)
+box = (torch.tensor(T.BBOX[0]), torch.tensor(T.BBOX[1]))
+
+def train(mods, render, tv_loss, opt):
+    emb, coarse, fine, sh, qfn = mods
+    kw = dict(N_samples=s_c, embed_fn=emb, retraw=True, perturb=0., N_importance=s_f, network_fine=fine, white_bkgd=True, raw_noise_std=0.)
+    evals = []
+    for step, (rays, rgb) in enumerate(batches, start=1):
+        ret = render(t(rays).to(DEV), coarse, qfn, **kw)
+        opt.zero_grad()
+        tgt = t(rgb).to(DEV)
+        loss = img2mse(ret["rgb_map"], tgt) + img2mse(ret["rgb0"], tgt) + 1e-10 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum())
+        torch.manual_seed(step)
+        tv = sum(tv_loss(emb.embeddings[i], 16, 512, i, log2T, n_levels=16) for i in range(16))
+        (loss + 1e-6 * tv).backward()
+        opt.step()
+        for g in opt.param_groups:
+            g["lr"] = lr * (0.1 ** (step / 10000.0))
+        if step in evals_at:
+            with torch.no_grad():
+                out = render(t(test_rays).to(DEV), coarse, qfn, **kw)
+            evals.append(T.psnr(out["rgb_map"].cpu().numpy(), test_rgb))
+    return evals
+
+torch.set_default_tensor_type('torch.cuda.FloatTensor')
+ref = ref_loader.load("cuda")
+torch.manual_seed(123)
+e0 = ref.HashEmbedder((box[0].to(DEV), box[1].to(DEV)), log2_hashmap_size=log2T).to(DEV)
+c0, f0 = ref.NeRFSmall(**geo).to(DEV), ref.NeRFSmall(**geo).to(DEV)
+init = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in (e0, c0, f0)]
+res = {}
+for run in range(2):
+    r_emb = ref.HashEmbedder((box[0].to(DEV), box[1].to(DEV)), log2_hashmap_size=log2T).to(DEV)
+    r_c, r_f, r_sh = ref.NeRFSmall(**geo).to(DEV), ref.NeRFSmall(**geo).to(DEV), ref.SHEncoder()
+    for m, sd in zip((r_emb, r_c, r_f), init):
+        m.load_state_dict(sd)
+    r_opt = ref.RAdam([{"params": list(r_c.parameters()) + list(r_f.parameters()), "weight_decay": 1e-6}, {"params": list(r_emb.parameters()), "eps": 1e-15}], lr=lr, betas=(0.9, 0.99))
+    r_q = lambda i, v, fn: ref.run_network(i, v, fn, embed_fn=r_emb, embeddirs_fn=r_sh, netchunk=1 << 16)
+    res[f"ref{run}"] = train((r_emb, r_c, r_f, r_sh, r_q), ref.render_rays, ref.total_variation_loss, r_opt)
+    print(f"ref{run}", np.round(res[f"ref{run}"], 3), "mean", np.mean(res[f"ref{run}"]), flush=True)
+torch.set_default_tensor_type('torch.FloatTensor')
+for run in range(2):
+    emb = HashEmbedder(box, log2_hashmap_size=log2T).to(DEV)
+    c, f, sh = NeRFSmall(**geo).to(DEV), NeRFSmall(**geo).to(DEV), SHEncoder()
+    for m, sd in zip((emb, c, f), init):
+        m.load_state_dict(sd)
+    opt = RAdam([{"params": list(c.parameters()) + list(f.parameters()), "weight_decay": 1e-6}, {"params": list(emb.parameters()), "eps": 1e-15}], lr=lr, betas=(0.9, 0.99))
+    q = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+    res[f"ours{run}"] = train((emb, c, f, sh, q), render_rays, total_variation_loss, opt)
+    print(f"ours{run}", np.round(res[f"ours{run}"], 3), "mean", np.mean(res[f"ours{run}"]), flush=True)
