@@ -266,7 +266,8 @@ def test_psnr_parity_against_the_reference_on_the_same_gpu():
     0.1 dB.  The reference is bit-reproducible run to run on this GPU; this package's scatter uses atomics, and training
     amplifies their summation-order noise chaotically: single evaluations of two of OUR runs differ by up to 0.3 dB
     while PSNR still climbs 0.05 dB per step (tools/exp_psnr_spread.py), so the comparison averages 20 evaluations
-    over the last 100 steps on 4096 held-out rays (observed |difference| of the means: 0.01-0.04 dB)."""
+    over the last 100 steps on 4096 held-out rays and over three of our runs (observed single-run differences:
+    -0.05 .. +0.09 dB)."""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
@@ -331,20 +332,26 @@ def test_psnr_parity_against_the_reference_on_the_same_gpu():
     finally:
         torch.set_default_tensor_type('torch.FloatTensor')
 
-    # ---- this package, from the same initial parameters
-    emb = HashEmbedder(box, log2_hashmap_size=log2T).to(DEV)
-    coarse, fine, sh = NeRFSmall(**geo).to(DEV), NeRFSmall(**geo).to(DEV), SHEncoder()
-    emb.load_state_dict(init["emb"])
-    coarse.load_state_dict(init["coarse"])
-    fine.load_state_dict(init["fine"])
-    opt = RAdam([{"params": list(coarse.parameters()) + list(fine.parameters()), "weight_decay": 1e-6},
-                 {"params": list(emb.parameters()), "eps": 1e-15}], lr=lr, betas=(0.9, 0.99), fused_zero_grad=True)
-    qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
-    psnr_ours, first_ours = train((emb, coarse, fine, sh, qfn), render_rays, total_variation_loss, opt)
+    # ---- this package, from the same initial parameters: three runs (the scatter's atomics make every run a slightly
+    # different trajectory; the reference's run is bit-reproducible)
+    ours = []
+    for _run in range(3):
+        emb = HashEmbedder(box, log2_hashmap_size=log2T).to(DEV)
+        coarse, fine, sh = NeRFSmall(**geo).to(DEV), NeRFSmall(**geo).to(DEV), SHEncoder()
+        emb.load_state_dict(init["emb"])
+        coarse.load_state_dict(init["coarse"])
+        fine.load_state_dict(init["fine"])
+        opt = RAdam([{"params": list(coarse.parameters()) + list(fine.parameters()), "weight_decay": 1e-6},
+                     {"params": list(emb.parameters()), "eps": 1e-15}], lr=lr, betas=(0.9, 0.99), fused_zero_grad=True)
+        qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+        p_run, first_ours = train((emb, coarse, fine, sh, qfn), render_rays, total_variation_loss, opt)
+        assert abs(first_ours - first_ref) <= 2e-5 * abs(first_ref)
+        ours.append(p_run)
+    psnr_ours = float(np.mean(ours))
 
     print(f"PSNR (mean of {len(evals_at)} evaluations, steps {evals_at[0]}..{evals_at[-1]}): ours {psnr_ours:.3f} dB, "
-          f"reference on the same GPU {psnr_ref:.3f} dB; "
+          f"reference on the same GPU {psnr_ref:.3f} dB; our runs {np.round(ours, 3)}; "
           f"first loss {first_ours:.6f} / {first_ref:.6f}")
-    assert abs(first_ours - first_ref) <= 2e-5 * abs(first_ref)
     assert psnr_ref > 15.0, "the synthetic scene should be learnable in this many steps"
     assert abs(psnr_ours - psnr_ref) <= 0.1
+    assert max(abs(p_ - psnr_ref) for p_ in ours) <= 0.25
