@@ -141,6 +141,8 @@ dp_reduce_update_kernel(float* const* __restrict__ grads, float* __restrict__ gr
   }
 }
 
+int g_dp_grid_per_sm = 8;  // hn_set_tuning("dp_grid_per_sm"): CTAs of 256 threads per SM for the exchange kernel
+
 }  // namespace hn
 
 extern "C" {
@@ -166,7 +168,7 @@ int hn_dp_reduce_update(void* const* grad_ptrs_dev, float* grad_mc, void* const*
   const int64_t end = begin + chunk < n ? begin + chunk : n;
   if (end <= begin) return 0;
   const int64_t want = (((end - begin) >> 2) + 255) / 256;
-  const int64_t cap = (int64_t)hn::sm_count() * 8;
+  const int64_t cap = (int64_t)hn::sm_count() * (hn::g_dp_grid_per_sm > 0 ? hn::g_dp_grid_per_sm : 8);
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   float* const* g = reinterpret_cast<float* const*>(grad_ptrs_dev);
   float* const* p = reinterpret_cast<float* const*>(param_ptrs_dev);

@@ -53,6 +53,7 @@ HN_API int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *                                    hn_mlp_bwd_workspace_bytes() follows the selection: query it after changing it
  *   "mlp_dw_nbuf"                    weight-gradient kernel: 1 = two CTAs/SM, one staging buffer (default); 2 = one
  *                                    CTA/SM, two buffers
+ *   "dp_grid_per_sm"                 CTAs per SM of hn_dp_reduce_update (default 8)
  *   "mlp_fwd_one_cta", "mlp_dw_ablate"   profiling only (occupancy / phase ablations; the latter breaks results)
  * Unknown keys return HN_EINVAL.  The knobs are PROCESS-GLOBAL and unsynchronised: set them before the threads that
  * launch kernels start (they exist for sweeps and A/B runs, not for per-call configuration). */
