@@ -680,7 +680,7 @@ def run_ours(args):
                 "fwd": {"ms": round(fwd_ms, 4), "gbs": round(n * BYTES_PER_SAMPLE_FWD / fwd_ms / 1e6, 1)},
                 "bwd": {"ms": round(bwd_ms, 4), "gbs": round(n * BYTES_PER_SAMPLE_BWD / bwd_ms / 1e6, 1)},
                 "sort": {"ms": round(sort_ms, 4), "grid_res": grid_res,
-                         "note": "counting sort of the points by grid cell; 5 small kernels, counted in the step"},
+                         "note": "counting sort of the points by grid cell (histogram, scan, partition with one global cursor per bin, per-bin local sort), counted in the step"},
                 "step_frac_of_hbm": round(n * (BYTES_PER_SAMPLE_FWD + BYTES_PER_SAMPLE_BWD)
                                           / (sort_ms + fwd_ms + bwd_ms) / 1e6 / peak, 4),
                 "traffic_source": "profiles/traffic.json (dram__bytes_read + write per launch from the ncu --set full "

@@ -60,9 +60,9 @@ SIGNATURES = {
     "hn_radam_step": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _d, _d, _d, _i, _f, _i, _p]),
 }
 
-# kernels launched per entry point (1 unless listed): hn_hash_sort_points = hist + 3 scan kernels + partition +
-# local sort (two-level form)
-KERNELS_PER_CALL = {"hn_hash_sort_points": 6, "hn_mlp_bwd": 2}  # hn_mlp_bwd: image prep + fused kernel
+# kernels launched per entry point (1 unless listed): hn_hash_sort_points = histogram + scan + partition + local sort
+# (two-level form; its memset node is not counted)
+KERNELS_PER_CALL = {"hn_hash_sort_points": 4, "hn_mlp_bwd": 2}  # hn_mlp_bwd: image prep + fused kernel
 
 _lib = None
 launches = 0  # number of CUDA kernels launched through call() (bench.py reports it as gpu_launches)

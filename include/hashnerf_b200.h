@@ -45,7 +45,7 @@ HN_API int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   "hash_bwd_agg"                   warp-aggregated scatter: -1 = sorted / ordered points only, 0 = never, 1 = always
  *   "hash_agg_max_heads"             aggregate a level only if a warp's 32 lanes form at most this many runs (24)
  *   "hash_level_major"               -1 = level-major grid for caller-ordered points, tile-major for sorted; 0/1 force
- *   "hash_sort_two_level"            1 = two-level counting sort (default), 0 = single-pass sort
+ *   "hash_sort_two_level"            1 = two-level counting sort, one global cursor per bin (default), 0 = single-pass sort
  *   "hash_div_hoist"                 1 = hoisted-reciprocal cell-index division (default), 0 = per-point true division
  *   "mlp_impl"                       1 = tcgen05 tensor-core MLP (default), 0 = FFMA fp32 MLP
  *   "mlp_bwd_impl"                   tcgen05 backward: 1 = one fused kernel, bf16 hi+lo operands, weight gradients
@@ -95,7 +95,8 @@ HN_API int hn_hash_encode_bwd_ordered(const float* x, const float* dy, const flo
  * the scatter sums lanes that share a voxel in-warp before issuing atomics -- and read dy / write out, keep at
  * the ORIGINAL rows, so results are indistinguishable from the plain calls (forward bit-identical, backward
  * up to atomic summation order).  workspace: hn_hash_sort_workspace_bytes(N, grid_res) bytes, 16-byte aligned;
- * xs4: [N] float4.  N < 2^32. */
+ * xs4: [N] float4.  N < 2^32.  The order of the points INSIDE one grid cell (and the workspace contents) may differ
+ * from call to call: slots are taken with atomics. */
 HN_API int64_t hn_hash_sort_workspace_bytes(int64_t N, int grid_res);
 HN_API int hn_hash_sort_points(const float* x, const float* bbox, int64_t N, int grid_res, void* workspace,
                                float* xs4, void* stream);
