@@ -1,5 +1,8 @@
 """Face exchange between x-adjacent runs in the aggregated scatter (hash_pair_min_heads / hash_pair_direct):
-time and agreement with the plain aggregated scatter, on sorted uniform points and on ray-ordered samples."""
+time and agreement with the plain aggregated scatter, on sorted uniform points and on ray-ordered samples.
+
+The exchange was slower everywhere and its kernel code was not kept: this script needs the two tuning
+keys of that experiment and is here as the record of what was measured, not as a runnable tool."""
 import json, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "hashnerf-pytorch_b200")); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
