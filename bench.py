@@ -75,10 +75,13 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def time_loop(fn, steps, warmup, dist=None):
-    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks."""
+def time_loop(fn, steps, warmup, dist=None, finish=None):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events, max over ranks.
+    ``finish``: joins whatever the last step left running on a side stream, inside the timed region."""
     for _ in range(warmup):
         fn()
+    if finish is not None:
+        finish()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -86,6 +89,8 @@ def time_loop(fn, steps, warmup, dist=None):
     e0.record()
     for _ in range(steps):
         fn()
+    if finish is not None:
+        finish()
     e1.record()
     if dist is not None:
         dist.barrier()
@@ -310,7 +315,11 @@ def workload_config(args, n_points):
             "e2e_readback": "a training pipeline keeps features and gradients on the device: the per-step result read "
                             "back is the 16 per-level gradient sums (64 B), not the 2.1 GB feature tensor",
             "parallelism": (f"dp{args.gpus} (points sharded; table gradient all-reduced "
-                            + ("in 4 level buckets, each overlapping the next bucket's scatter" if args.bucket_overlap
+                            + ("once after the scatter, on a side stream under the next step's point sort, joined before "
+                               "that step clears the gradient" if getattr(args, "buckets_used", None) == "pipelined"
+                               else f"in level buckets {args.buckets_used}, each exchanged on a side stream while the "
+                               "next is scattered" if getattr(args, "buckets_used", None)
+                               else "in 4 level buckets, each overlapping the next bucket's scatter" if args.bucket_overlap
                                else "once after the scatter") + f"; exchange: {getattr(args, 'exchange_used', args.exchange)})")
             if args.gpus > 1 else "single"}
 
@@ -493,10 +502,12 @@ def fern_frame_extra(dev):
     return time_loop(frame, 3, 1) / 3
 
 
-def dp_self_check(dist, dev, world, bwd, dflat, tables):
+def dp_self_check(dist, dev, world, bwd, dflat, tables, exchange_step=None):
     """N > 1, once before timing: (1) the all-reduced table gradient's checksum equals the sum of the per-rank
     checksums gathered separately; (2) after one fused RAdam step on the reduced gradient (1/world folded in) the
-    parameters are bit-identical on every rank.  Works on copies: the timed state is untouched."""
+    parameters are bit-identical on every rank; (3) the scatter + exchange exactly as the timed step issues them
+    (``exchange_step``: our symmetric-memory kernels, bucketed or not) leave the same reduced gradient in place as
+    the NCCL all-reduce of a copy.  Works on copies: the timed state is untouched."""
     from radam import RAdam
     dflat.zero_()
     bwd()
@@ -518,8 +529,17 @@ def dp_self_check(dist, dev, world, bwd, dflat, tables):
     hs = [torch.zeros_like(h) for _ in range(world)]
     dist.all_gather(hs, h)
     ok_par = all(int(t.item()) == int(hs[0].item()) for t in hs)
+    ok_ex = True
+    if exchange_step is not None:
+        dflat.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        exchange_step()
+        torch.cuda.synchronize(dev)
+        ok_ex = float((dflat - red).abs().max().item()) <= 1e-5 * float(red.abs().max().item())
     dflat.zero_()
-    return "ok" if (ok_sum and ok_par) else f"FAILED (checksum {ok_sum}, parameters identical {ok_par})"
+    return "ok" if (ok_sum and ok_par and ok_ex) else \
+        f"FAILED (checksum {ok_sum}, parameters identical {ok_par}, own exchange equals NCCL {ok_ex})"
 
 
 def train_shape_roofline(dev, emb, peak, steps=10):
@@ -616,8 +636,18 @@ def run_ours(args):
     def bwd():
         ops.hash_encode_backward_sorted(out_holder["xs4"], dy, box, res, L, F, log2T, dflat)
 
-    reducer, buckets = None, []
-    if dist is not None and args.bucket_overlap:
+    reducer, buckets, overlap, pipelined = None, [], None, False
+    if dist is not None and sar is not None and args.buckets != "none":
+        from hn_b200.dp import OverlappedTableReducer
+        overlap = OverlappedTableReducer(sar, L)
+        if args.buckets == "pipelined":
+            pipelined = True
+        else:
+            buckets = [tuple(int(v) for v in part.split("-")) for part in args.buckets.split(",")]
+            assert buckets[0][0] == 0 and buckets[-1][1] == L and all(a[1] == b[0] for a, b in zip(buckets, buckets[1:])), \
+                "--buckets must tile [0, L)"
+        args.buckets_used = args.buckets
+    elif dist is not None and sar is None and args.bucket_overlap:
         from hn_b200.dp import BucketedTableReducer
         reducer = BucketedTableReducer(L)
         buckets = BucketedTableReducer.buckets(L, 4)
@@ -625,11 +655,29 @@ def run_ours(args):
     def step():
         # what HashEmbedder.forward + autograd backward launch for this many points: counting sort by grid
         # cell, sorted gather, zero-grad, warp-aggregated scatter (+ the DP all-reduce)
+        if pipelined:
+            # the exchange of step s runs through the switch on a side stream while step s+1 sorts ITS points (the
+            # sort depends on the batch only); it is joined before the gradient buffer is cleared and before the
+            # gather reads the tables an optimizer would have updated from it
+            sort()
+            overlap.wait()
+            dflat.zero_()
+            fwd()
+            bwd()
+            overlap.reduce_levels(0, L)
+            return
         dflat.zero_()
         sort()
         fwd()
         if dist is None:
             bwd()
+        elif overlap is not None:
+            # level buckets over symmetric memory: bucket b is exchanged through the switch (side stream) while
+            # bucket b+1 is scattered; only the last bucket's exchange is exposed
+            for b, e in buckets:
+                ops.hash_encode_backward_sorted(out_holder["xs4"], dy, box, res, L, F, log2T, dflat, levels=(b, e))
+                overlap.reduce_levels(b, e)
+            overlap.wait()
         elif reducer is None:
             bwd()
             if sar is not None:
@@ -647,14 +695,27 @@ def run_ours(args):
     dp_check = None
     if dist is not None:
         out_holder["xs4"] = ops.hash_sort_points(x, box, grid_res)
-        dp_check = dp_self_check(dist, dev, world, bwd, dflat, tables)
+        def exchange_step():   # the scatter + exchange part of step(), on an already zeroed dflat
+            if pipelined:
+                bwd()
+                overlap.reduce_levels(0, L)
+                overlap.wait()
+            elif overlap is not None:
+                for b, e in buckets:
+                    ops.hash_encode_backward_sorted(out_holder["xs4"], dy, box, res, L, F, log2T, dflat, levels=(b, e))
+                    overlap.reduce_levels(b, e)
+                overlap.wait()
+            else:
+                bwd()
+                sar.all_reduce()
+        dp_check = dp_self_check(dist, dev, world, bwd, dflat, tables, exchange_step if sar is not None else None)
 
     # ---- headline: device-resident inputs
     clocks = ClockSampler(local)
     launches0 = _lib.launches
     if rank == 0:
         clocks.start()
-    total_ms = time_loop(step, args.steps, args.warmup, dist)
+    total_ms = time_loop(step, args.steps, args.warmup, dist, finish=overlap.wait if overlap is not None else None)
     clock_report = clocks.stop() if rank == 0 else None
     gpu_launches = (_lib.launches - launches0) * args.steps // (args.steps + args.warmup)
     ms_per_step = total_ms / args.steps
@@ -899,8 +960,15 @@ def main():
                     help="N > 1: also time the data-parallel training step as one CUDA graph with the NCCL all-reduces "
                          "captured inside (opt-in: keeps the default run free of collective capture)")
     ap.add_argument("--bucket-overlap", action="store_true",
-                    help="N > 1: all-reduce the table gradient in 4 level buckets overlapped with the scatter instead "
-                         "of once after it (measured slower: splitting the scatter costs more than the overlap hides)")
+                    help="N > 1, --exchange nccl: all-reduce the table gradient in 4 level buckets overlapped with the "
+                         "scatter instead of once after it (measured slower with NCCL: splitting the scatter costs "
+                         "more than the overlap hides)")
+    ap.add_argument("--buckets", default="pipelined",
+                    help="N > 1, symmetric-memory exchange.  'pipelined' (default): the exchange of step s runs on a "
+                         "side stream under the point sort of step s+1 and is joined before that step clears the "
+                         "gradient / gathers; 'none': one exchange after the scatter, nothing overlapped; 'b-e,b-e': "
+                         "level buckets, each exchanged while the next is scattered (measured slower: the split "
+                         "scatter re-reads dY)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "nccl"],
                     help="N > 1: how gradients are exchanged -- our one-pass kernel over symmetric memory (auto: with "
                          "fall-back to NCCL if symmetric memory cannot be set up) or the NCCL library all-reduce")

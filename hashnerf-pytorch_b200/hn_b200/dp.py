@@ -309,6 +309,7 @@ class SymmetricAllReduce:
         self._g_tab, self._sig_tab = self.buf.ptr_table(0), self.signals.ptr_table(0)
         self._hp = torch.tensor([0, 0, 0, 0, 0, 1.0, -1.0, 0], dtype=torch.float32, device=device)
         self._epoch = 0
+        self._tabs = {0: self._g_tab}   # peer-pointer tables per range start
         self.multicast = bool(self.buf.multicast_ptr)
         dist.barrier(group=group)
         torch.cuda.synchronize(device)
@@ -317,13 +318,54 @@ class SymmetricAllReduce:
     def tensor(self) -> torch.Tensor:
         return self.buf.tensor
 
-    def all_reduce(self):
+    def all_reduce(self, begin: int = 0, end: Optional[int] = None):
+        """Sum elements [begin, end) of the buffer over the ranks, on the current stream.  Every rank must make the
+        same sequence of calls (the barrier epochs count calls); begin and end - begin are multiples of 4."""
+        n = self.buf.tensor.numel()
+        end = n if end is None else int(end)
+        begin = int(begin)
+        if not (0 <= begin <= end <= n) or (begin & 3) or ((end - begin) & 3):
+            raise ValueError(f"range [{begin}, {end}) must lie in [0, {n}) with begin and length multiples of 4")
+        if end == begin:
+            return
+        tab = self._tabs.get(begin)
+        if tab is None:
+            tab = self._tabs[begin] = self.buf.ptr_table(begin)
         self._epoch += 1
         s = ops._stream()
         _lib_call("hn_dp_barrier", self._sig_tab.data_ptr(), self.rank, self.world, 0, self._epoch, s)
-        _lib_call("hn_dp_reduce_update", self._g_tab.data_ptr(), self.buf.mc_ptr(0) or None, None, None, None, None,
-                  self.rank, self.world, self.buf.tensor.numel(), self._hp.data_ptr(), s)
+        _lib_call("hn_dp_reduce_update", tab.data_ptr(), self.buf.mc_ptr(begin) or None, None, None, None, None,
+                  self.rank, self.world, end - begin, self._hp.data_ptr(), s)
         _lib_call("hn_dp_barrier", self._sig_tab.data_ptr(), self.rank, self.world, 1, self._epoch, s)
+
+
+class OverlappedTableReducer:
+    """The table-gradient exchange in level buckets over symmetric memory, overlapped with the scatter.
+
+    The flat gradient ``[L * 2^T * F]`` is level-major; after the scatter of levels ``[b, e)`` has been enqueued
+    (``ops.hash_encode_backward_sorted(..., levels=(b, e))``) :meth:`reduce_levels` enqueues the one-pass exchange
+    of that slice (hn_dp_barrier + hn_dp_reduce_update) on a high-priority side stream behind an event, so it runs
+    through the switch while the compute stream scatters the next bucket; only the last bucket's exchange is
+    exposed.  All exchanges go through ONE side stream in call order, which keeps the barrier epochs in step on
+    every rank.  :meth:`wait` joins the side stream."""
+
+    def __init__(self, sar: SymmetricAllReduce, n_levels: int):
+        self.sar, self.n_levels = sar, int(n_levels)
+        dev = sar.tensor.device
+        self._stream = torch.cuda.Stream(device=dev, priority=-1)   # above the compute stream: its few CTAs go first
+        self._ev = torch.cuda.Event()
+
+    def reduce_levels(self, begin: int, end: int) -> None:
+        if not (0 <= begin <= end <= self.n_levels):
+            raise ValueError(f"level range [{begin}, {end}) outside [0, {self.n_levels})")
+        slab = self.sar.tensor.numel() // self.n_levels
+        self._ev.record(torch.cuda.current_stream(self._stream.device))   # the bucket's scatter has been enqueued
+        self._stream.wait_event(self._ev)
+        with torch.cuda.stream(self._stream):
+            self.sar.all_reduce(begin * slab, end * slab)
+
+    def wait(self) -> None:
+        torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
 
 
 def _lib_call(name, *args):

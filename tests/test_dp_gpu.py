@@ -259,3 +259,70 @@ def test_fused_exchange_two_gpus():
         p.join(timeout=60)
     print(results)
     assert all(msg.startswith("ok") for _r, msg in results), results
+
+
+def _overlap_worker(rank, world, port, q):
+    """The table-gradient exchange in level buckets on a side stream (hn_b200.dp.OverlappedTableReducer) must leave
+    the same sum on every rank as NCCL's all-reduce of the per-rank gradients, also over several steps (the barrier
+    epochs count calls)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hashnerf-pytorch_b200"))
+        from hn_b200 import ops
+        from hn_b200.dp import OverlappedTableReducer, SymmetricAllReduce
+        L, F, log2T, n = 16, 2, 14, 1 << 19
+        box = torch.tensor([-1.5] * 3 + [1.5] * 3, device=dev)
+        res = torch.tensor([16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512.0], device=dev)
+        sar = SymmetricAllReduce(L * (1 << log2T) * F, dev)
+        ov = OverlappedTableReducer(sar, L)
+        dflat = sar.tensor
+        msg = "ok"
+        for step, buckets in enumerate(([(0, 12), (12, 16)], [(0, 4), (4, 8), (8, 16)], [(0, 16)])):
+            g = torch.Generator(device=dev).manual_seed(100 * step + rank)
+            x = torch.rand(n, 3, device=dev, generator=g) * 3 - 1.5
+            dy = torch.randn(n, L * F, device=dev, generator=g)
+            xs4 = ops.hash_sort_points(x, box, 64)
+            own = torch.zeros_like(dflat)
+            ops.hash_encode_backward_sorted(xs4, dy, box, res, L, F, log2T, own)
+            want = own.clone()
+            dist.all_reduce(want)
+            dflat.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            for b, e in buckets:
+                ops.hash_encode_backward_sorted(xs4, dy, box, res, L, F, log2T, dflat, levels=(b, e))
+                ov.reduce_levels(b, e)
+            ov.wait()
+            torch.cuda.synchronize(dev)
+            err = (dflat - want).abs().max().item() / want.abs().max().item()
+            if not err <= 1e-5:
+                msg = f"step {step} buckets {buckets}: relative difference {err:.3e}"
+                break
+        with pytest.raises(ValueError):
+            sar.all_reduce(2, 10)
+        q.put((rank, msg))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, f"{type(exc).__name__}: {exc}\n{traceback.format_exc()}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_overlapped_table_exchange_two_gpus():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    print(results)
+    assert all(msg.startswith("ok") for _r, msg in results), results
