@@ -26,8 +26,27 @@ constexpr int oW4 = oW3 + 64 * 64;     //  8 x 64 (N padded 3 -> 8)
 constexpr int kImg = oW4 + 8 * 64;     // 9728 floats per image (hi, then lo)
 constexpr uint32_t kColD = 0, kColAhi = 64, kColAlo = 128, kTmemCols = 256;
 
-__device__ __forceinline__ void stage_matrix(const float* __restrict__ w, int rows, int cols, int rows_pad, int K,
-                                             float* __restrict__ hi_img, float* __restrict__ lo_img) {
+// kTile threads; shapes are compile-time so that the loop unrolls and eight weight loads are in flight per thread
+// (one load per trip left every CTA's prologue at ~8 us of L2 round trips: 76 dependent trips)
+template <int ROWS, int COLS, int ROWS_PAD, int K>
+__device__ __forceinline__ void stage_matrix(const float* __restrict__ w, float* __restrict__ hi_img,
+                                             float* __restrict__ lo_img) {
+  static_assert((ROWS_PAD * K) % kTile == 0, "whole trips");
+#pragma unroll 8
+  for (int j = 0; j < (ROWS_PAD * K) / kTile; ++j) {
+    const int i = j * kTile + (int)threadIdx.x;
+    const int n = i / K, k = i % K;
+    const float v = (n < ROWS && k < COLS) ? __ldg(w + n * COLS + k) : 0.f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    hi_img[canon(n, k, K)] = __uint_as_float(hi);
+    lo_img[canon(n, k, K)] = __uint_as_float(lo);
+  }
+}
+
+// run-time shapes, any CTA size (the two-kernel backward's prologue)
+__device__ __forceinline__ void stage_matrix_dyn(const float* __restrict__ w, int rows, int cols, int rows_pad, int K,
+                                                 float* __restrict__ hi_img, float* __restrict__ lo_img) {
   for (int i = threadIdx.x; i < rows_pad * K; i += blockDim.x) {
     const int n = i / K, k = i % K;
     const float v = (n < rows && k < cols) ? __ldg(w + n * cols + k) : 0.f;
@@ -41,11 +60,11 @@ __device__ __forceinline__ void stage_matrix(const float* __restrict__ w, int ro
 __device__ __forceinline__ void stage_weights(const float* __restrict__ w, float* __restrict__ smem) {
   float* hi = smem;
   float* lo = smem + kImg;
-  stage_matrix(w + kG0, 64, 32, 64, 32, hi + oW0, lo + oW0);
-  stage_matrix(w + kG1, 16, 64, 16, 64, hi + oW1, lo + oW1);
-  stage_matrix(w + kG2, 64, 31, 64, 32, hi + oW2, lo + oW2);
-  stage_matrix(w + kG3, 64, 64, 64, 64, hi + oW3, lo + oW3);
-  stage_matrix(w + kG4, 3, 64, 8, 64, hi + oW4, lo + oW4);
+  stage_matrix<64, 32, 64, 32>(w + kG0, hi + oW0, lo + oW0);
+  stage_matrix<16, 64, 16, 64>(w + kG1, hi + oW1, lo + oW1);
+  stage_matrix<64, 31, 64, 32>(w + kG2, hi + oW2, lo + oW2);
+  stage_matrix<64, 64, 64, 64>(w + kG3, hi + oW3, lo + oW3);
+  stage_matrix<3, 64, 8, 64>(w + kG4, hi + oW4, lo + oW4);
 }
 
 // One layer: D = A . W^T as 3 x (K/8) MMAs; small terms first.  Called by ONE thread: its instruction stream is
@@ -283,10 +302,10 @@ mlp_tc_bwd_delta_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   {
     float* hi = smem;
     float* lo = smem + kImgBwd;
-    stage_matrix(weights + kG0, 64, 32, 64, 32, hi + oW0, lo + oW0);
-    stage_matrix(weights + kG1, 16, 64, 16, 64, hi + oW1, lo + oW1);
-    stage_matrix(weights + kG2, 64, 31, 64, 32, hi + oW2, lo + oW2);
-    stage_matrix(weights + kG3, 64, 64, 64, 64, hi + oW3, lo + oW3);
+    stage_matrix_dyn(weights + kG0, 64, 32, 64, 32, hi + oW0, lo + oW0);
+    stage_matrix_dyn(weights + kG1, 16, 64, 16, 64, hi + oW1, lo + oW1);
+    stage_matrix_dyn(weights + kG2, 64, 31, 64, 32, hi + oW2, lo + oW2);
+    stage_matrix_dyn(weights + kG3, 64, 64, 64, 64, hi + oW3, lo + oW3);
     stage_transposed(weights + kG4, 64, 3, 0, 64, 64, 8, hi + oT4, lo + oT4);
     stage_transposed(weights + kG3, 64, 64, 0, 64, 64, 64, hi + oT3, lo + oT3);
     stage_transposed(weights + kG2, 31, 64, 16, 15, 16, 64, hi + oT2, lo + oT2);

@@ -28,6 +28,8 @@
 #include "mlp_tc_common.cuh"
 
 namespace hn {
+extern int g_mlp_dw_ablate;  // mlp_tc.cu (profiling only)
+
 namespace tc {
 
 // ---- bf16 canonical K-major weight images [N][K], in elements; hi image, then lo image -----------------------
@@ -42,6 +44,8 @@ constexpr int bT1 = bT2 + 16 * 64;     // 64 x 16  (n = k, kk = j)     = W1[j][k
 constexpr int bT0 = bT1 + 64 * 16;     // 32 x 64  (n = k, kk = j)     = W0[j][k]
 constexpr int kImg16 = bT0 + 32 * 64;  // 18432 elements per image
 constexpr uint32_t kImgBytes = (uint32_t)kImg16 * 2u * 2u;  // 73,728
+constexpr int kGTotal = kG4 + 3 * 64;                       // 9344 weight-gradient floats
+constexpr int64_t kGTotalBytes = (int64_t)kGTotal * 4;
 static_assert(kImgBytes % 1024 == 0, "operand buffers behind the images must stay 1024-byte aligned");
 
 __device__ __forceinline__ float image_value(const float* __restrict__ w, int mat, int n, int k) {
@@ -248,7 +252,7 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
                         int64_t views_stride, int64_t pts_per_view, const uint16_t* __restrict__ images,
                         const uint8_t* __restrict__ keep, const uint32_t* __restrict__ gates,
                         const float* __restrict__ dout, int64_t N, float* __restrict__ d_enc,
-                        float* __restrict__ dweights, int aligned) {
+                        float* __restrict__ partials, int aligned, int ablate) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t bars[5];  // [0], [1]: layer MMAs of context 0 / 1; [2], [3]: their dW MMAs; [4]: images
@@ -509,10 +513,27 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   ctx_sync(sync_id);
   wait_dw(c);
   fence_after_sync();
-  if (tile0 < n_tiles) {
+  // ---- the CTA's weight gradient -> partials[blockIdx.x][9344]; mlp_dw_reduce_kernel sums the rows.  (Atomics on
+  // dweights from every context cost 37-42 us when the 296 contexts of a small batch finish together: 2.7 M atomics on
+  // 9344 addresses.)  Context 1 parks its 80 values per thread in shared memory -- the operand buffers are free now,
+  // and thread t of either context holds the same (row, column) elements -- context 0 adds its own and stores.
+  float* stage = reinterpret_cast<float*>(smem + kImgBytes) + t;   // [80][128]: conflict-free
+  __syncthreads();  // both contexts have drained their MMAs: context 0's operand buffers may be overwritten
+  if (ctx == 1 && !(ablate & 1)) {
+    float v[16];
+#pragma unroll
+    for (int c0 = 0; c0 < (int)fAccCols; c0 += 16) {
+      tmem_ld16(acc_row + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) stage[(c0 + i) * kTile] = v[i];
+    }
+  }
+  __syncthreads();
+  if (ctx == 0 && !(ablate & 1)) {
     // M = 64 accumulator rows: row m sits in lane (m % 16) + 32 (m / 16) of its lane half; a thread with
     // lane < 16 holds row 16 warp + lane of the first accumulator of each column range, the others row
     // 16 warp + lane - 16 of the second one.
+    float* part = partials + (size_t)blockIdx.x * kGTotal;
     const bool second = lane >= 16;
     const int m = warp * 16 + (lane & 15);
     float v[16];
@@ -520,18 +541,27 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
     for (int c0 = 0; c0 < 64; c0 += 16) {
       tmem_ld16(acc_row + c0, v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int col = c0 + i;
-        if (!second) atomicAdd(dweights + kG3 + m * 64 + col, v[i]);              // dW3[j = m][k = col]
-        else if (col < 32) atomicAdd(dweights + kG0 + m * 32 + col, v[i]);        // dW0[j = m][k = col]
-        else if (col - 32 < 31) atomicAdd(dweights + kG2 + m * 31 + (col - 32), v[i]);  // dW2[j = m][c]
+      for (int i = 0; i < 16; ++i) v[i] += stage[(c0 + i) * kTile];
+      if (!second) {                                  // dW3[j = m][k = c0 ..]
+        float4* dst = reinterpret_cast<float4*>(part + kG3 + m * 64 + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else if (c0 < 32) {                           // dW0[j = m][k = c0 ..]
+        float4* dst = reinterpret_cast<float4*>(part + kG0 + m * 32 + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {                                        // dW2[j = m][c = c0 - 32 ..], rows of 31
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 - 32 + i < 31) part[kG2 + m * 31 + (c0 - 32 + i)] = v[i];
       }
     }
     tmem_ld16(acc_row + 64, v);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      if (!second) atomicAdd(dweights + kG1 + i * 64 + m, v[i]);                  // dW1^T[k = m][j = i]
-      else if (i < 3) atomicAdd(dweights + kG4 + i * 64 + m, v[i]);               // dW4^T[k = m][c = i]
+      const float x = v[i] + stage[(64 + i) * kTile];
+      if (!second) part[kG1 + i * 64 + m] = x;        // dW1^T[k = m][j = i]
+      else if (i < 3) part[kG4 + i * 64 + m] = x;     // dW4^T[k = m][c = i]
     }
   }
   fence_before_sync();
@@ -539,9 +569,47 @@ mlp_tc_bwd_fused_kernel(const float* __restrict__ enc, int64_t enc_stride, const
   if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
 }
 
+// dweights[j] += sum over the CTAs' partial rows; 32 float4 outputs per CTA, its 8 warps split the rows
+__global__ void __launch_bounds__(256)
+mlp_dw_reduce_kernel(const float* __restrict__ partials, int n_rows, float* __restrict__ dweights) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j4 = blockIdx.x * 32 + lane;  // float4 index into the 9344 floats
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j4 < kGTotal / 4) {
+#pragma unroll 4
+    for (int r = warp; r < n_rows; r += 8) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partials + (size_t)r * kGTotal) + j4);
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && j4 < kGTotal / 4) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      s.x += red[w][lane].x;
+      s.y += red[w][lane].y;
+      s.z += red[w][lane].z;
+      s.w += red[w][lane].w;
+    }
+    float* d = dweights + 4 * j4;   // accumulate: the caller's buffer may already hold the other pass's gradient
+    atomicAdd(d, s.x);
+    atomicAdd(d + 1, s.y);
+    atomicAdd(d + 2, s.z);
+    atomicAdd(d + 3, s.w);
+  }
+}
+
 }  // namespace tc
 
-int64_t mlp_tc_bwd_fused_workspace_bytes() { return (int64_t)tc::kImgBytes; }
+// weight images + one partial weight-gradient row per CTA
+int64_t mlp_tc_bwd_fused_workspace_bytes() {
+  return (int64_t)tc::kImgBytes + (int64_t)sm_count() * tc::kGTotalBytes;
+}
 
 int mlp_tc_bwd_fused(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride, int64_t pts_per_view,
                      const float* weights, const uint8_t* keep, const uint32_t* gates, const float* dout, int64_t N,
@@ -560,20 +628,29 @@ int mlp_tc_bwd_fused(const float* enc, int64_t enc_stride, const float* views, i
     done_dev = dev;
   }
   uint16_t* images = reinterpret_cast<uint16_t*>(workspace);
-  tc::mlp_bwd_prep_kernel<<<(tc::kImg16 + 255) / 256, 256, 0, stream>>>(weights, images);
-  int rc = check_launch("mlp_bwd_prep_kernel");
-  if (rc) return rc;
+  int rc = 0;
+  if (!(g_mlp_dw_ablate & 2)) {
+    tc::mlp_bwd_prep_kernel<<<(tc::kImg16 + 255) / 256, 256, 0, stream>>>(weights, images);
+    rc = check_launch("mlp_bwd_prep_kernel");
+    if (rc) return rc;
+  }
   const int64_t tiles = (N + tc::kTile - 1) / tc::kTile;
   const int64_t cap = (int64_t)sm_count();
   const int64_t want = (tiles + 1) / 2;  // two tile contexts per CTA
   const unsigned grid = (unsigned)(want < cap ? want : cap);
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + tc::kImgBytes);
   if (gates != nullptr)
     tc::mlp_tc_bwd_fused_kernel<true><<<grid, 2 * tc::kTile, tc::kFusedSmemBytes, stream>>>(
-        enc, enc_stride, views, views_stride, pts_per_view, images, keep, gates, dout, N, d_enc, dweights, aligned);
+        enc, enc_stride, views, views_stride, pts_per_view, images, keep, gates, dout, N, d_enc, partials, aligned,
+        g_mlp_dw_ablate);
   else
     tc::mlp_tc_bwd_fused_kernel<false><<<grid, 2 * tc::kTile, tc::kFusedSmemBytes, stream>>>(
-        enc, enc_stride, views, views_stride, pts_per_view, images, keep, gates, dout, N, d_enc, dweights, aligned);
-  return check_launch("mlp_tc_bwd_fused_kernel");
+        enc, enc_stride, views, views_stride, pts_per_view, images, keep, gates, dout, N, d_enc, partials, aligned,
+        g_mlp_dw_ablate);
+  if ((rc = check_launch("mlp_tc_bwd_fused_kernel"))) return rc;
+  if (g_mlp_dw_ablate & 1) return 0;
+  tc::mlp_dw_reduce_kernel<<<(tc::kGTotal / 4 + 31) / 32, 256, 0, stream>>>(partials, (int)grid, dweights);
+  return check_launch("mlp_dw_reduce_kernel");
 }
 
 }  // namespace hn

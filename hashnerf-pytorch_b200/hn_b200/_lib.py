@@ -62,7 +62,7 @@ SIGNATURES = {
 
 # kernels launched per entry point (1 unless listed): hn_hash_sort_points = histogram + scan + partition + local sort
 # (two-level form; its memset node is not counted)
-KERNELS_PER_CALL = {"hn_hash_sort_points": 4, "hn_mlp_bwd": 2}  # hn_mlp_bwd: image prep + fused kernel
+KERNELS_PER_CALL = {"hn_hash_sort_points": 4, "hn_mlp_bwd": 3}  # hn_mlp_bwd: image prep + fused kernel + dW row sum
 
 _lib = None
 launches = 0  # number of CUDA kernels launched through call() (bench.py reports it as gpu_launches)

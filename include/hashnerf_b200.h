@@ -142,7 +142,9 @@ HN_API int hn_mlp_fwd(const float* enc, int64_t enc_stride, const float* views, 
  * dweights [9344] (ACCUMULATED).  No gradient w.r.t. views on this path (directions are data).
  * gates (may be NULL): the masks hn_mlp_fwd wrote for the same inputs; NULL = take the sign of the recomputed
  * pre-activations (exact for the fp32 / 3xTF32 implementations, within 1e-5 of a kink for the fused bf16x2 one).
- * workspace: caller-provided scratch of hn_mlp_bwd_workspace_bytes(N) bytes, 16-byte aligned. */
+ * workspace: caller-provided scratch of hn_mlp_bwd_workspace_bytes(N) bytes, 16-byte aligned (fused implementation:
+ * the bf16 weight images + one partial weight-gradient row per CTA, summed into dweights by a second small kernel --
+ * no atomics from the main kernel, and a summation order that is the same on every call). */
 HN_API int64_t hn_mlp_bwd_workspace_bytes(int64_t N);
 HN_API int hn_mlp_bwd(const float* enc, int64_t enc_stride, const float* views, int64_t views_stride,
                int64_t pts_per_view, const float* weights, const uint8_t* keep, const uint32_t* gates,
