@@ -106,20 +106,41 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
   }
 }
 
+// Bitonic network over a[0..n) (n a power of two) by one warp: every lane owns whole compare-exchange PAIRS
+// (pair q <-> i = q with a zero bit inserted at log2 j, partner i | j), so all 32 lanes work in every trip.
+__device__ __forceinline__ void bitonic_sort_warp(float* __restrict__ a, int n, int lane) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 4
+      for (int q = lane; q < (n >> 1); q += 32) {
+        const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+        const int partner = i | j;
+        const float x = a[i], y = a[partner];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) {
+          a[i] = y;
+          a[partner] = x;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // Fused hierarchical resampling for one ray per warp (run_nerf_helpers.py:547-552, 568):
 //   mids = .5 (z[1:] + z[:-1]);  samples = sample_pdf(mids, weights[1:-1], u);  merged = sort(cat(z, samples));
 //   z_std = std(samples, unbiased=False).
-// Shared memory per warp: cdf[S-1] | mids[S-1] | sort buffer[npad].
+// Shared memory per warp: cdf[S-1] | mids[S-1] | sort buffer[bufsz = max(npad, S + npad_s)].
 __global__ void __launch_bounds__(128)
 resample_kernel(const float* __restrict__ z, const float* __restrict__ weights, const float* __restrict__ u,
-                const float* __restrict__ u_det, int64_t R, int S, int Ni, int npad, float* __restrict__ samples,
-                float* __restrict__ merged, float* __restrict__ z_std) {
+                const float* __restrict__ u_det, int64_t R, int S, int Ni, int npad, int npad_s, int bufsz,
+                float* __restrict__ samples, float* __restrict__ merged, float* __restrict__ z_std) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (r >= R) return;
   const int nb = S - 1;
-  float* cdf = smem + (size_t)warp * (2 * nb + npad);
+  float* cdf = smem + (size_t)warp * (2 * nb + bufsz);
   float* mids = cdf + nb;
   float* buf = mids + nb;
   const float* zr = z + r * S;
@@ -146,7 +167,6 @@ resample_kernel(const float* __restrict__ z, const float* __restrict__ weights, 
   }
   // sort buffer: the S coarse depths, then the Ni new samples, then +inf padding
   for (int i = lane; i < S; i += 32) buf[i] = __ldg(zr + i);
-  for (int i = S + Ni + lane; i < npad; i += 32) buf[i] = __int_as_float(0x7f800000);
   __syncwarp();
 
   float s1 = 0.f;
@@ -184,22 +204,46 @@ resample_kernel(const float* __restrict__ z, const float* __restrict__ weights, 
     if (lane == 0) z_std[r] = sqrtf(s2 / (float)Ni);
   }
   __syncwarp();
-  for (int k = 2; k <= npad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < npad; i += 32) {
-        const int partner = i ^ j;
-        if (partner > i) {
-          const float x = buf[i], y = buf[partner];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) {
-            buf[i] = y;
-            buf[partner] = x;
-          }
-        }
+  // The coarse depths come sorted (stratified sampling) and only the Ni new samples are not: sort those alone
+  // (a network over npad_s <= 2 Ni values instead of npad >= S + Ni) and merge by rank -- an element's place in
+  // the merged row is its index in its own sequence plus the number of elements of the other sequence before it
+  // (strictly smaller for the depths, smaller-or-equal for the samples: a bijection also with ties).  The result
+  // is the same sorted row; rows whose depths are not sorted, or that hold a NaN, take the full network.
+  bool fast = npad_s > 0;
+  for (int i = lane; i < S - 1; i += 32) fast = fast && (buf[i] <= buf[i + 1]);
+  for (int k = lane; k < Ni; k += 32) fast = fast && (buf[S + k] == buf[S + k]);
+  fast = __all_sync(kFullMask, fast);
+  if (fast) {
+    float* sb = buf + S;
+    for (int i = Ni + lane; i < npad_s; i += 32) sb[i] = __int_as_float(0x7f800000);
+    __syncwarp();
+    bitonic_sort_warp(sb, npad_s, lane);
+    float* out = merged + r * (S + Ni);
+    for (int i = lane; i < S; i += 32) {
+      const float v = buf[i];
+      int lo = 0, hi = Ni;
+      while (lo < hi) {  // samples strictly below v
+        const int mid = (lo + hi) >> 1;
+        if (sb[mid] < v) lo = mid + 1;
+        else hi = mid;
       }
-      __syncwarp();
+      out[i + lo] = v;
     }
+    for (int k = lane; k < Ni; k += 32) {
+      const float v = sb[k];
+      int lo = 0, hi = S;
+      while (lo < hi) {  // depths at or below v
+        const int mid = (lo + hi) >> 1;
+        if (buf[mid] <= v) lo = mid + 1;
+        else hi = mid;
+      }
+      out[k + lo] = v;
+    }
+    return;
   }
+  for (int i = S + Ni + lane; i < npad; i += 32) buf[i] = __int_as_float(0x7f800000);
+  __syncwarp();
+  bitonic_sort_warp(buf, npad, lane);
   for (int i = lane; i < S + Ni; i += 32) merged[r * (S + Ni) + i] = buf[i];
 }
 
@@ -286,14 +330,17 @@ int hn_resample(const float* z, const float* weights, const float* u, const floa
   HN_REQUIRE(z && weights && samples && merged && (u || u_det), "hn_resample: null pointer");
   int npad = 2;
   while (npad < S + Ni) npad <<= 1;
+  int npad_s = 2;
+  while (npad_s < Ni) npad_s <<= 1;
+  const int bufsz = npad > S + npad_s ? npad : S + npad_s;
   const int warps = 4;
-  const size_t smem = (size_t)warps * (2 * (S - 1) + npad) * sizeof(float);
+  const size_t smem = (size_t)warps * (2 * (S - 1) + bufsz) * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(hn::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return hn::fail((int)e, "cudaFuncSetAttribute(resample_kernel)");
   }
   hn::resample_kernel<<<(unsigned)((R + warps - 1) / warps), warps * 32, smem, (cudaStream_t)stream>>>(
-      z, weights, u, u_det, R, S, Ni, npad, samples, merged, z_std);
+      z, weights, u, u_det, R, S, Ni, npad, npad_s, bufsz, samples, merged, z_std);
   return hn::check_launch("resample_kernel");
 }
 

@@ -54,6 +54,8 @@ SIGNATURES = {
     "hn_tv_loss_bwd_levels": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "hn_ndc_rays": (_i, [_i, _i, _d, _d, _p, _l, _p, _l, _l, _p, _p, _p]),
     "hn_sample_rays": (_i, [_p, _i, _p, _i, _i, _f, _f, _f, _f, _f, _f, _p, _l, _p, _p, _p, _p]),
+    "hn_mse_fwd": (_i, [_p, _p, _l, _p, _p]),
+    "hn_mse_bwd": (_i, [_p, _p, _l, _p, _p, _p, _p]),
     "hn_dp_barrier": (_i, [_p, _i, _i, _i, C.c_uint32, _p]),
     "hn_dp_reduce_update": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _l, _p, _p]),
     "hn_radam_step_dev": (_i, [_p, _p, _p, _p, _l, _p, _p]),

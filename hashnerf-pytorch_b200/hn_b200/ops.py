@@ -505,6 +505,38 @@ class MLPFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------
+# photometric loss
+# ----------------------------------------------------------------------------------------------
+class MSEFn(torch.autograd.Function):
+    """mean((a - b) ** 2) of two fp32 CUDA tensors of one shape: one launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        dev = _need_cuda(a, b)
+        a, b = _f32c(a), _f32c(b)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with _on(dev):
+            _lib.call("hn_mse_fwd", a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        need_a, need_b = ctx.needs_input_grad
+        gout = _f32c(gout)
+        da = torch.empty_like(a) if need_a else None
+        db = torch.empty_like(b) if need_b else None
+        with _on(a.device):
+            _lib.call("hn_mse_bwd", a.data_ptr(), b.data_ptr(), a.numel(), gout.data_ptr(), _ptr(da), _ptr(db), _stream())
+        return da, db
+
+
+def mse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    return MSEFn.apply(a, b)
+
+
+# ----------------------------------------------------------------------------------------------
 # compositing
 # ----------------------------------------------------------------------------------------------
 class CompositeFn(torch.autograd.Function):

@@ -27,7 +27,13 @@ from embedding.hash_encoding import HashEmbedder, SHEncoder
 from models import NeRF, NeRFSmall, NeRFGradient  # noqa: F401
 
 # Misc (run_nerf_helpers.py:24-26)
-img2mse = lambda x, y: torch.mean((x - y) ** 2)
+def img2mse(x, y):
+    """mean((x - y) ** 2) (run_nerf_helpers.py:24).  Same-shape fp32 CUDA tensors: one launch each way (hn_mse_fwd /
+    hn_mse_bwd) instead of three forward and four backward; anything else: the reference's expression."""
+    if (isinstance(x, torch.Tensor) and isinstance(y, torch.Tensor) and x.is_cuda and y.is_cuda
+            and x.dtype == torch.float32 and y.dtype == torch.float32 and x.shape == y.shape and x.numel() > 0):
+        return ops.mse(x, y)
+    return torch.mean((x - y) ** 2)
 # the reference's torch.Tensor([10.]) lands on the default tensor type's device (CUDA after run_nerf.py:725); built
 # on x's device here so that the helper also works without that global switch -- same value, same [1] shape
 mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], dtype=torch.float32, device=x.device))

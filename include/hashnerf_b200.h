@@ -223,6 +223,12 @@ HN_API int hn_sample_rays(const float* images, int channels, const float* poses,
                           float* rays, float* target, int32_t* pix, void* stream);
 
 /* ---- section 8f "next" row 2: total_variation_loss : loss.py:11-43 ---------------------------------- */
+/* img2mse (run_nerf_helpers.py:24): out[0] = mean((a - b)^2) over n floats, one CTA, fixed summation order.
+ * Backward: da = gout[0] * 2 (a - b) / n, db = -da; either of da / db may be NULL. */
+HN_API int hn_mse_fwd(const float* a, const float* b, int64_t n, float* out, void* stream);
+HN_API int hn_mse_bwd(const float* a, const float* b, int64_t n, const float* gout, float* da, float* db,
+                      void* stream);
+
 /* One hash level: table [2^log2T, F]; origin = int64[3] on the device (the random cube corner drawn at
  * loss.py:25); cube = cube size (loss.py:22).  fwd writes out[0] = (sum of squared forward differences over the
  * (cube+1)^3 hashed vertices) / cube.  bwd ACCUMULATES gout[0] * d out / d table into dtable [2^log2T, F]. */

@@ -658,6 +658,45 @@ def test_resample_fused(R, S, Ni, det):
     close(z_std, torch.std(samples, dim=-1, unbiased=False), 1e-4, atol=1e-6)
 
 
+def test_resample_unsorted_depths_and_duplicates():
+    """The merge-by-rank path needs sorted coarse depths; rows that are not (or that repeat values between the
+    depths and the new samples) must still come out as sort(cat(z, samples))."""
+    from hn_b200 import ops
+    rs = np.random.RandomState(11)
+    R, S, Ni = 37, 24, 40
+    z = np.sort(2 + 4 * rs.rand(R, S).astype(np.float32), -1)
+    z[::3] = z[::3, ::-1]                       # every third row descending: takes the full network
+    z[1, 5] = z[1, 4]                           # a tie inside the depths
+    w = (rs.rand(R, S).astype(np.float32)) ** 2
+    w[2, :] = 0.0                               # all-empty row: every denominator below 1e-5
+    u = rs.rand(R, Ni).astype(np.float32)
+    u[4, :] = 0.5                               # Ni identical samples
+    samples, merged, _ = ops.resample(g32(z), g32(w), Ni, u=g32(u))
+    bit_equal(merged, torch.sort(torch.cat([g32(z), samples], -1), -1).values)
+
+
+def test_img2mse_one_launch():
+    """img2mse on CUDA goes through hn_mse_fwd / hn_mse_bwd: value and both gradients against the reference's
+    expression (run_nerf_helpers.py:24)."""
+    from run_nerf_helpers import img2mse
+    for shape in [(1024, 3), (7,), (5000, 3)]:
+        gen = torch.Generator(device=DEV).manual_seed(len(shape))
+        a = torch.rand(*shape, device=DEV, generator=gen).requires_grad_(True)
+        b = torch.rand(*shape, device=DEV, generator=gen).requires_grad_(True)
+        got = img2mse(a, b)
+        (3.0 * got).backward()
+        ga, gb = a.grad.clone(), b.grad.clone()
+        a.grad = b.grad = None
+        want = torch.mean((a - b) ** 2)
+        (3.0 * want).backward()
+        close(got, want, 1e-6)
+        close(ga, a.grad, 1e-6, atol=1e-9)
+        close(gb, b.grad, 1e-6, atol=1e-9)
+    # CPU tensors keep the reference's expression
+    x, y = torch.rand(4, 3), torch.rand(4, 3)
+    assert torch.equal(img2mse(x, y), torch.mean((x - y) ** 2))
+
+
 def test_sort_concat_rows():
     from hn_b200 import ops
     for na, nb, R in [(64, 128, 100), (1, 1, 3), (5, 0, 4), (24, 40, 48), (700, 1300, 5), (64, 64, 1000)]:
