@@ -6,7 +6,7 @@ from hn_b200 import ops, _lib
 from sweep_hash import timeit
 dev = torch.device("cuda:0"); gen = torch.Generator(device=dev).manual_seed(0)
 box = torch.tensor([-1.5] * 3 + [1.5] * 3, device=dev)
-variants = [int(v) for v in os.environ.get("VARIANTS", "1,2,3,4").split(",")]
+variants = [int(v) for v in os.environ.get("VARIANTS", "1,0").split(",")]
 for logn in (24, 22, 20):
     n = 1 << logn
     x = torch.rand(n, 3, device=dev, generator=gen) * 3 - 1.5
