@@ -427,6 +427,31 @@ class TVSweepFn(torch.autograd.Function):
         return (None,) * 7 + tuple(target.view(L, -1, F).unbind(0))
 
 
+class TVSweepPartsFn(torch.autograd.Function):
+    """The same launch as TVSweepFn, but the L terms come back as L separate scalars: a training loop that adds
+    them up one by one (``sum(total_variation_loss(...) for i in range(16))``, run_nerf.py:628-635) then has no
+    ``select`` node per level, whose backward is a zero-fill + copy + accumulate -- 48 tiny launches per step."""
+
+    @staticmethod
+    def forward(ctx, flat_tables, origins, cubes, max_cube, log2T, F, sink, *levels):
+        ctx.set_materialize_grads(False)
+        out = TVSweepFn.forward(ctx, flat_tables, origins, cubes, max_cube, log2T, F, sink, *levels)
+        return tuple(out.unbind(0))
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        L = ctx.meta[0]
+        given = [g for g in gouts if g is not None]
+        if not given:
+            return (None,) * (7 + L)
+        if len(given) == L:
+            gout = torch.stack([g.reshape(()) for g in gouts])
+        else:
+            zero = torch.zeros((), dtype=given[0].dtype, device=given[0].device)
+            gout = torch.stack([zero if g is None else g.reshape(()) for g in gouts])
+        return TVSweepFn.backward(ctx, gout)
+
+
 # ----------------------------------------------------------------------------------------------
 # spherical harmonics
 # ----------------------------------------------------------------------------------------------

@@ -52,8 +52,9 @@ _GEOMETRY = weakref.WeakKeyDictionary()  # HashEmbedder -> cached per-level cube
 ops.pre_capture_hooks.append(_SWEEPS.clear)   # a cached sweep keeps an autograd graph alive across a graph capture
 
 
-def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels):
-    """All levels' TV terms of ``owner`` as one [L] tensor (a fresh random cube per level, loss.py:25)."""
+def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels, parts=False):
+    """All levels' TV terms of ``owner`` as one [L] tensor -- or, ``parts``, as L scalars behind one autograd node --
+    (a fresh random cube per level, loss.py:25)."""
     geo = _GEOMETRY.get(owner)
     flat = owner.flat_tables()
     dev = flat.device
@@ -75,8 +76,8 @@ def _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, 
         origins = torch.stack([torch.randint(0, sp, (3,), device=dev) for sp in spans])
     levels = owner._level_weights()
     sink = owner.grad_sink() if (torch.is_grad_enabled() and levels[0].requires_grad) else None
-    return ops.TVSweepFn.apply(flat, origins, cubes, max_cube, int(log2_hashmap_size), int(flat.shape[-1]), sink,
-                               *levels)
+    fn = ops.TVSweepPartsFn if parts else ops.TVSweepFn
+    return fn.apply(flat, origins, cubes, max_cube, int(log2_hashmap_size), int(flat.shape[-1]), sink, *levels)
 
 
 def total_variation_sweep(embed_fn):
@@ -104,7 +105,7 @@ def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2
                 or sw.versions != [w._version for w in owner._level_weights()]):
             sw = _Sweep()
             sw.key = key
-            sw.vec = _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels)
+            sw.vec = _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels, parts=True)
             sw.versions = [w._version for w in owner._level_weights()]
             _SWEEPS[owner] = sw
         sw.last = level

@@ -1064,6 +1064,22 @@ def test_tv_loss_sweep_matches_per_level_and_caches():
         (one * gout[l]).backward()
     want = torch.stack([e.weight.grad for e in emb.embeddings])
     close(got, want, GRAD_RTOL, atol=1e-9)
+    # the L-scalars form (what the per-level calls are served from): same values, same gradients, also when only
+    # some of the terms take part in the loss
+    for used in (range(L), (0, 3, 15)):
+        for e in emb.embeddings:
+            e.weight.grad = None
+        parts = ops.TVSweepPartsFn.apply(flat, origins, cubes, max(c for _, c in geo), 12, 2, None, *emb._level_weights())
+        assert len(parts) == L and all(p.dim() == 0 for p in parts)
+        bit_equal(torch.stack(parts), vec.detach())
+        sum(parts[l] * gout[l] for l in used).backward()
+        got_p = torch.stack([e.weight.grad if e.weight.grad is not None else torch.zeros_like(e.weight)
+                             for e in emb.embeddings])
+        mask = torch.zeros(L, device=DEV)
+        mask[list(used)] = 1.0
+        close(got_p, want * mask[:, None, None], GRAD_RTOL, atol=1e-9)
+    for e in emb.embeddings:
+        e.weight.grad = None
 
     def sweep_calls(levels, grad=True):
         before = _lib.launches
