@@ -45,7 +45,8 @@ def level_owner(embedding_module):
     if entry is None:
         return None, None
     owner = entry[0]()
-    if owner is None or owner.embeddings[entry[1]] is not embedding_module:
+    # plain dict lookups (nn.ModuleList.__getitem__ is ~2 us, and the training loop asks 16 times per step)
+    if owner is None or owner._modules['embeddings']._modules.get(str(entry[1])) is not embedding_module:
         return None, None
     return owner, entry[1]
 

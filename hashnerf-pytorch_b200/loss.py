@@ -44,7 +44,7 @@ TV_FAST_DRAWS = False
 
 
 class _Sweep:
-    __slots__ = ("key", "vec", "last", "versions")
+    __slots__ = ("key", "vec", "last", "versions", "ptrs", "epoch")
 
 
 _SWEEPS = weakref.WeakKeyDictionary()    # HashEmbedder -> its current sweep (kept off the module: no pickling issues)
@@ -96,17 +96,20 @@ def total_variation_loss(embeddings, min_resolution, max_resolution, level, log2
 
     if (TV_SWEEP and owner is not None and weight.is_cuda and own_level == level
             and owner.n_levels == n_levels and owner.log2_hashmap_size == log2_hashmap_size):
-        # a sweep is only reused for the same arguments, grad mode and tables (storage, torch version counters, and
-        # the update counter of this package's RAdam, whose kernels write through raw pointers)
-        key = (min_resolution, max_resolution, log2_hashmap_size, n_levels, torch.is_grad_enabled(),
-               owner._level_weights()[0].data_ptr(), ops.param_epoch[0])
+        # a sweep is only reused for the same arguments and grad mode, and a level's term only while that level's
+        # table is unchanged (storage, torch version counter, and the update counter of this package's RAdam, whose
+        # kernels write through raw pointers)
+        args = (min_resolution, max_resolution, log2_hashmap_size, n_levels, torch.is_grad_enabled())
         sw = _SWEEPS.get(owner)
-        if (sw is None or sw.key != key or level <= sw.last
-                or sw.versions != [w._version for w in owner._level_weights()]):
+        if (sw is None or sw.key != args or level <= sw.last or sw.epoch != ops.param_epoch[0]
+                or sw.versions[level] != weight._version or sw.ptrs[level] != weight.data_ptr()):
             sw = _Sweep()
-            sw.key = key
-            sw.vec = _sweep_terms(owner, key, min_resolution, max_resolution, log2_hashmap_size, n_levels, parts=True)
-            sw.versions = [w._version for w in owner._level_weights()]
+            sw.key = args
+            sw.epoch = ops.param_epoch[0]
+            sw.vec = _sweep_terms(owner, args, min_resolution, max_resolution, log2_hashmap_size, n_levels, parts=True)
+            ws = owner._level_weights()
+            sw.versions = [w._version for w in ws]
+            sw.ptrs = [w.data_ptr() for w in ws]
             _SWEEPS[owner] = sw
         sw.last = level
         return sw.vec[level]

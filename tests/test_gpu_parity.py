@@ -1071,7 +1071,7 @@ def test_tv_loss_sweep_matches_per_level_and_caches():
             e.weight.grad = None
         parts = ops.TVSweepPartsFn.apply(flat, origins, cubes, max(c for _, c in geo), 12, 2, None, *emb._level_weights())
         assert len(parts) == L and all(p.dim() == 0 for p in parts)
-        bit_equal(torch.stack(parts), vec.detach())
+        close(torch.stack(parts), vec.detach(), 1e-5)   # the forward sums with atomics: not bit-reproducible
         sum(parts[l] * gout[l] for l in used).backward()
         got_p = torch.stack([e.weight.grad if e.weight.grad is not None else torch.zeros_like(e.weight)
                              for e in emb.embeddings])
@@ -1104,7 +1104,10 @@ def test_tv_loss_sweep_matches_per_level_and_caches():
     assert sweep_calls([9])[1] == 1, "tables changed (RAdam kernel): the sweep must be re-evaluated"
     with torch.no_grad():
         emb.embeddings[2].weight.mul_(1.0)                                      # torch in-place op: version bump
-    assert sweep_calls([10])[1] == 1
+    assert sweep_calls([10])[1] == 0, "another level's table changed: level 10's term is still the sweep's"
+    with torch.no_grad():
+        emb.embeddings[11].weight.mul_(1.0)
+    assert sweep_calls([11])[1] == 1, "the level's own table changed: the sweep must be re-evaluated"
 
 
 def test_grad_sink_accumulation_semantics():
