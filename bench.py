@@ -932,11 +932,28 @@ def run_ours(args):
             finally:
                 import loss as _loss_mod
                 _loss_mod.TV_FAST_DRAWS = False
+        # the eager loop again, with render_rays replayed as CUDA graphs UNDER the drop-in API (HN_AUTO_GRAPH=1: what an
+        # unmodified run_nerf.py gets with that variable set); switches the process to a side stream, hence last
+        from hn_b200 import autograph
+        try:
+            autograph.enable(True)
+            autograph.ensure_stream(dev)
+            for n_rand in (1024, 8192):
+                rps, ms = train_step_extra(dev, n_rand, steps=20, warmup=6)
+                extra[f"train_rays_per_s_nrand{n_rand}_auto_graph"] = round(rps, 1)
+                extra[f"train_ms_per_step_nrand{n_rand}_auto_graph"] = round(ms, 3)
+            extra["auto_graph_stats"] = dict(autograph.stats)
+        except Exception as exc:
+            extra["train_auto_graph"] = f"failed: {type(exc).__name__}: {exc}"[:200]
+        finally:
+            autograph.shutdown()
         extra["train_step"] = ("render_rays 64+128 samples/ray, perturb=1, white_bkgd, mse+sparsity, backward, RAdam"
                                "; eager = the drop-in API driven like run_nerf.py:608-642 incl. the 16 TV-loss terms, cuda_graph "
                                "= hn_b200.graph.GraphedTrainStep replaying render+loss+backward+RAdam(+zero-grad) on given rays (no TV); "
                                "cuda_graph_full = the same graph with the on-device ray batcher (pixel sampling, ray "
-                               "generation, target gather from 8 resident 400x400 images) and the 16 TV terms inside")
+                               "generation, target gather from 8 resident 400x400 images) and the 16 TV terms inside; auto_graph = the eager "
+                               "loop statements unchanged, render_rays replayed as a forward and a backward CUDA graph behind "
+                               "one autograd node (hn_b200.autograph, HN_AUTO_GRAPH=1)")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

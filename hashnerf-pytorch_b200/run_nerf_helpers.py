@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F  # noqa: F401  (star-exported like the reference)
 
-from hn_b200 import ops
+from hn_b200 import autograph, ops
 from radam import RAdam
 from ray_util import get_rays, get_rays_np, get_ndc_rays  # noqa: F401
 from embedding.embedder import Embedder
@@ -121,6 +121,8 @@ def create_nerf(args):
     """Instantiate encoders, coarse/fine networks and the optimizer; reload the newest checkpoint.
 
     Returns (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer)."""
+    if autograph.ENABLED and torch.cuda.is_available() and torch.device(device).type == "cuda":
+        autograph.ensure_stream(device)   # HN_AUTO_GRAPH=1: everything from here on runs on one non-default stream
     embed_fn, input_ch = get_embedder(args.multires, args, i=args.i_embed)
     embedding_params = list(embed_fn.parameters()) if args.i_embed == 1 else []
     if isinstance(embed_fn, nn.Module):
@@ -261,7 +263,25 @@ def render_rays(ray_batch,
 
     ray_batch [R, 8 or 11] = (origin, direction, near, far[, unit view direction]).  Returns the
     reference's dict: rgb_map, depth_map, acc_map, sparsity_loss[, raw][, rgb0, depth0, acc0,
-    sparsity_loss0, z_std]."""
+    sparsity_loss0, z_std].
+
+    With ``HN_AUTO_GRAPH=1`` (hn_b200.autograph) repeated training calls of one signature are replayed as two CUDA
+    graphs (forward, backward) behind one autograd node; everything else runs the statements below."""
+    if (autograph.ENABLED and torch.is_grad_enabled() and ray_batch.is_cuda and not pytest and not DEBUG
+            and not verbose):
+        kw = dict(network_fn=network_fn, network_query_fn=network_query_fn, N_samples=N_samples, embed_fn=embed_fn,
+                  retraw=retraw, lindisp=lindisp, perturb=perturb, N_importance=N_importance,
+                  network_fine=network_fine, white_bkgd=white_bkgd, raw_noise_std=raw_noise_std)
+        ret = autograph.render_rays(_render_rays_eager, ray_batch, kw)
+        if ret is not None:
+            return ret
+    return _render_rays_eager(ray_batch, network_fn, network_query_fn, N_samples, embed_fn, retraw, lindisp, perturb,
+                              N_importance, network_fine, white_bkgd, raw_noise_std, verbose, pytest)
+
+
+def _render_rays_eager(ray_batch, network_fn, network_query_fn, N_samples, embed_fn=None, retraw=False, lindisp=False,
+                       perturb=0., N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0.,
+                       verbose=False, pytest=False):
     rb = ray_batch if (ray_batch.dtype == torch.float32 and ray_batch.is_contiguous()) else ray_batch.float().contiguous()
     R, width = rb.shape
     rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]

@@ -51,7 +51,12 @@ def main(argv):
     sys.path[:0] = [os.path.join(HERE, "standins"), os.path.join(ROOT, "hashnerf-pytorch_b200"), ref]
     sys.argv = [os.path.join(ref, "run_nerf.py"), "--config", cfg] + rest
     os.chdir(workdir)
-    runpy.run_path(os.path.join(ref, "run_nerf.py"), run_name="__main__")
+    try:
+        runpy.run_path(os.path.join(ref, "run_nerf.py"), run_name="__main__")
+    finally:
+        if os.environ.get("HN_AUTO_GRAPH") == "1":   # how often render_rays was replayed as CUDA graphs under the script
+            from hn_b200 import autograph
+            print("[autograph]", dict(autograph.stats), flush=True)
 
 
 if __name__ == "__main__":

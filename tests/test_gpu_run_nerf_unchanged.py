@@ -23,12 +23,24 @@ def _have_reference():
 
 
 @pytest.mark.skipif(not _have_reference(), reason="reference run_nerf.py not available (oracle/make_ref.py not run)")
-def test_reference_run_nerf_main_runs_unchanged(tmp_path):
+@pytest.mark.parametrize("auto_graph", [False, True])
+def test_reference_run_nerf_main_runs_unchanged(tmp_path, auto_graph):
+    """auto_graph: the same unmodified script with HN_AUTO_GRAPH=1 in the environment -- render_rays is then replayed
+    as a forward and a backward CUDA graph under the script's own loop (hn_b200.autograph)."""
     iters = 60
+    env = dict(os.environ, HN_AUTO_GRAPH="1" if auto_graph else "0")
     res = subprocess.run([sys.executable, HARNESS, str(tmp_path), "--iters", str(iters)], capture_output=True, text=True,
-                         timeout=900)
+                         timeout=900, env=env)
     tail = (res.stdout[-3000:] + "\n--- stderr ---\n" + res.stderr[-3000:])
     assert res.returncode == 0, tail
+    if auto_graph:
+        import ast
+        line = [l for l in res.stdout.splitlines() if l.startswith("[autograph]")]
+        assert line, tail
+        st = ast.literal_eval(line[-1][len("[autograph]"):].strip())
+        # precrop (10 iterations) and the full-image phase sample the same number of rays: one signature, one capture,
+        # everything after the warm-up calls replayed
+        assert st["failed"] == 0 and st["captures"] == 1 and st["eager"] == 3 and st["replays"] >= iters - 20, st
     logs = os.path.join(tmp_path, "logs")
     exp = [d for d in os.listdir(logs)]
     assert len(exp) == 1 and exp[0].startswith("harness_hashXYZ_sphereVIEW"), exp   # util.create_expname ran

@@ -200,6 +200,98 @@ def test_graphed_step_matches_eager_step():
     assert [opt_a.state[p]['step'] for p in params_a] == [opt_b.state[p]['step'] for p in params_b]
 
 
+def test_auto_graph_under_a_foreign_training_loop():
+    """hn_b200.autograph (HN_AUTO_GRAPH=1): the reference's loop statements (render_rays -> zero_grad -> loss incl. the
+    16 TV terms -> backward -> step), with last iteration's loss still referenced when render is called again, run
+    (a) eagerly and (b) with render_rays replayed as a forward and a backward CUDA graph behind one autograd node.
+    Same rays and targets per step, no jitter: loss curve and parameter trajectory must agree; a second forward
+    before the pending backward and a call under no_grad must fall back to the eager path."""
+    import cases
+    from embedding.hash_encoding import HashEmbedder
+    from embedding.spherical_harmonic import SHEncoder
+    from hn_b200 import autograph
+    from loss import total_variation_loss
+    from models import NeRFSmall
+    from radam import RAdam
+    from run_nerf_helpers import render_rays, run_network, img2mse
+    dev = torch.device("cuda:0")
+
+    def build():
+        torch.manual_seed(11)
+        emb = HashEmbedder((torch.tensor(cases.BBOX_UNIT[0]), torch.tensor(cases.BBOX_UNIT[1])), log2_hashmap_size=12)
+        with torch.no_grad():
+            for e in emb.embeddings:
+                e.weight.mul_(3000.0)
+        mk = lambda: NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                               input_ch=32, input_ch_views=16)
+        emb, coarse, fine, sh = emb.to(dev), mk().to(dev), mk().to(dev), SHEncoder()
+        opt = RAdam([{"params": list(coarse.parameters()) + list(fine.parameters()), "weight_decay": 1e-6},
+                     {"params": list(emb.parameters()), "eps": 1e-15}], lr=0.01, betas=(0.9, 0.99))
+        opt.fused_zero_grad = True
+        qfn = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+        kw = dict(network_fn=coarse, network_query_fn=qfn, N_samples=16, embed_fn=emb, retraw=True, perturb=0.,
+                  N_importance=16, network_fine=fine, white_bkgd=True)
+        params = list(emb.parameters()) + list(coarse.parameters()) + list(fine.parameters())
+        return emb, opt, kw, params
+
+    n_rays, n_steps = 64, 12
+    all_rays = torch.from_numpy(cases.rays(n_rays * n_steps, 21)).to(dev).reshape(n_steps, n_rays, -1)
+    targets = torch.rand(n_steps, n_rays, 3, generator=torch.Generator().manual_seed(4)).to(dev)
+
+    def run(emb, opt, kw):
+        losses, loss = [], None
+        for k in range(n_steps):
+            ret = render_rays(all_rays[k], **kw)             # `loss` of the previous iteration is still alive here
+            opt.zero_grad()
+            loss = img2mse(ret["rgb_map"], targets[k]) + img2mse(ret["rgb0"], targets[k]) \
+                + 1e-10 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum())
+            torch.manual_seed(100 + k)                       # same TV cubes in both runs
+            loss = loss + 1e-6 * sum(total_variation_loss(emb.embeddings[i], emb.base_resolution, emb.finest_resolution,
+                                                          i, emb.log2_hashmap_size, n_levels=emb.n_levels)
+                                     for i in range(emb.n_levels))
+            loss.backward()
+            opt.step()
+            losses.append(loss.detach().clone())
+        return torch.stack(losses).cpu().numpy()
+
+    emb_e, opt_e, kw_e, params_e = build()
+    le = run(emb_e, opt_e, kw_e)
+    torch.cuda.synchronize()
+
+    autograph.enable(True)
+    try:
+        assert autograph.ensure_stream(dev) is not None
+        before = dict(autograph.stats)
+        emb_g, opt_g, kw_g, params_g = build()
+        lg = run(emb_g, opt_g, kw_g)
+        torch.cuda.synchronize()
+        assert autograph.stats["failed"] == before["failed"], "the capture must succeed under a foreign loop"
+        assert autograph.stats["captures"] == before["captures"] + 1
+        assert autograph.stats["replays"] - before["replays"] == n_steps - autograph.WARMUP_CALLS
+        np.testing.assert_allclose(lg[:3], le[:3], rtol=1e-5)
+        np.testing.assert_allclose(lg, le, rtol=2e-3)
+        _e, _o, _k, params_0 = build()
+        start = torch.cat([p.detach().reshape(-1) for p in params_0]).clone()
+        fa = torch.cat([p.detach().reshape(-1) for p in params_g])
+        fb = torch.cat([p.detach().reshape(-1) for p in params_e])
+        update, diff = float((fb - start).norm()), float((fa - fb).norm())
+        assert update > 0 and diff <= 0.02 * update, f"auto-graphed and eager runs drifted: {diff:.3e} vs {update:.3e}"
+        # two forwards before a backward: the second one must not clobber the first one's activations
+        r1 = render_rays(all_rays[0], **kw_g)
+        n_replays = autograph.stats["replays"]
+        r2 = render_rays(all_rays[1], **kw_g)
+        assert autograph.stats["replays"] == n_replays, "a forward with a pending backward must run eagerly"
+        want1 = render_rays(all_rays[0], **kw_e)   # the eager model is at (almost) the same parameters
+        (r1["rgb_map"].sum() + r2["rgb_map"].sum()).backward()
+        with torch.no_grad():
+            r3 = render_rays(all_rays[0], **kw_g)
+        assert not r3["rgb_map"].requires_grad
+        assert float((r1["rgb_map"] - want1["rgb_map"]).abs().max()) < 0.05
+    finally:
+        autograph.shutdown()
+    assert torch.cuda.current_stream(dev) == torch.cuda.default_stream(dev)
+
+
 def test_full_graph_step_with_batcher_and_tv():
     """The complete step as one CUDA graph: on-device batch construction (hn_sample_rays), render, mse + sparsity +
     all TV terms (loss.total_variation_sweep, equal to the training loop's per-level sum), backward, RAdam with

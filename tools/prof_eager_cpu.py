@@ -21,8 +21,11 @@ def profiled(fn, steps, warmup, dist=None, finish=None):
     return orig(fn, steps, 1, dist, finish)
 
 bench.time_loop = profiled
+from hn_b200 import autograph
+if autograph.ENABLED:
+    autograph.ensure_stream(dev)
 rps, ms = bench.train_step_extra(dev, n_rand, steps=30, warmup=3)
 print(f"eager step {ms:.3f} ms")
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(35)
+pstats.Stats(pr, stream=s).sort_stats(os.environ.get("SORT", "tottime")).print_stats(40)
 print(s.getvalue()[:6000])

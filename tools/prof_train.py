@@ -17,5 +17,8 @@ if "SORT_MIN" in os.environ:
 for knob in ("hash_bwd_agg", "hash_fwd_lpg", "hash_bwd_lpg", "hash_agg_max_heads", "mlp_impl"):
     if knob.upper() in os.environ:
         _lib.set_tuning(knob, int(os.environ[knob.upper()]))
+from hn_b200 import autograph
+if autograph.ENABLED:          # HN_AUTO_GRAPH=1: the eager loop with render_rays replayed as CUDA graphs
+    autograph.ensure_stream(dev)
 rps, ms = bench.train_step_extra(dev, n_rand, steps=steps, warmup=int(os.environ.get("WARMUP", 2)), graphed=graphed)
-print(json.dumps({"n_rand": n_rand, "graphed": graphed, "ms_per_step": round(ms, 3), "rays_per_s": round(rps, 1)}))
+print(json.dumps({"n_rand": n_rand, "graphed": graphed, "auto_graph": dict(autograph.stats) if autograph.ENABLED else None, "ms_per_step": round(ms, 3), "rays_per_s": round(rps, 1)}))
