@@ -16,7 +16,7 @@ from run_nerf_helpers import render_rays, run_network, img2mse
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
 DEV = "cuda"
 log2T, s_c, s_f, n_rand, steps, lr = 19, 64, 128, 1024, int(os.environ.get("STEPS", 200)), 0.01
-evals_at = tuple(range(steps - 45, steps + 1, 5))
+evals_at = tuple(range(steps - 95, steps + 1, 5))
 batches = [T.scene_rays(n_rand, 500 + i) for i in range(steps)]
 test_rays, test_rgb = T.scene_rays(4096, 4242)
 geo = dict(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64, input_ch=32, input_ch_views=16)
@@ -50,7 +50,7 @@ e0 = ref.HashEmbedder((box[0].to(DEV), box[1].to(DEV)), log2_hashmap_size=log2T)
 c0, f0 = ref.NeRFSmall(**geo).to(DEV), ref.NeRFSmall(**geo).to(DEV)
 init = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in (e0, c0, f0)]
 res = {}
-for run in range(2):
+for run in range(int(os.environ.get("REF_RUNS", 1))):
     r_emb = ref.HashEmbedder((box[0].to(DEV), box[1].to(DEV)), log2_hashmap_size=log2T).to(DEV)
     r_c, r_f, r_sh = ref.NeRFSmall(**geo).to(DEV), ref.NeRFSmall(**geo).to(DEV), ref.SHEncoder()
     for m, sd in zip((r_emb, r_c, r_f), init):
@@ -60,12 +60,22 @@ for run in range(2):
     res[f"ref{run}"] = train((r_emb, r_c, r_f, r_sh, r_q), ref.render_rays, ref.total_variation_loss, r_opt)
     print(f"ref{run}", np.round(res[f"ref{run}"], 3), "mean", np.mean(res[f"ref{run}"]), flush=True)
 torch.set_default_tensor_type('torch.FloatTensor')
-for run in range(2):
-    emb = HashEmbedder(box, log2_hashmap_size=log2T).to(DEV)
-    c, f, sh = NeRFSmall(**geo).to(DEV), NeRFSmall(**geo).to(DEV), SHEncoder()
-    for m, sd in zip((emb, c, f), init):
-        m.load_state_dict(sd)
-    opt = RAdam([{"params": list(c.parameters()) + list(f.parameters()), "weight_decay": 1e-6}, {"params": list(emb.parameters()), "eps": 1e-15}], lr=lr, betas=(0.9, 0.99))
-    q = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
-    res[f"ours{run}"] = train((emb, c, f, sh, q), render_rays, total_variation_loss, opt)
-    print(f"ours{run}", np.round(res[f"ours{run}"], 3), "mean", np.mean(res[f"ours{run}"]), flush=True)
+from hn_b200 import _lib
+# our runs per implementation choice: is a PSNR gap to the reference trajectory chaos or a bias of one kernel?
+variants = {"default": {}, "mlp_fp32_ffma": {"mlp_impl": 0}, "mlp_bwd_3xtf32": {"mlp_bwd_impl": 0}}
+for name, knobs in variants.items():
+    for k, v in knobs.items():
+        _lib.set_tuning(k, v)
+    means = []
+    for run in range(int(os.environ.get("OUR_RUNS", 4))):
+        emb = HashEmbedder(box, log2_hashmap_size=log2T).to(DEV)
+        c, f, sh = NeRFSmall(**geo).to(DEV), NeRFSmall(**geo).to(DEV), SHEncoder()
+        for m, sd in zip((emb, c, f), init):
+            m.load_state_dict(sd)
+        opt = RAdam([{"params": list(c.parameters()) + list(f.parameters()), "weight_decay": 1e-6}, {"params": list(emb.parameters()), "eps": 1e-15}], lr=lr, betas=(0.9, 0.99))
+        q = lambda i, v, fn: run_network(i, v, fn, embed_fn=emb, embeddirs_fn=sh)
+        ev = train((emb, c, f, sh, q), render_rays, total_variation_loss, opt)
+        means.append(float(np.mean(ev)))
+    print(name, "run means", np.round(means, 3), "mean", round(float(np.mean(means)), 3), "vs ref", round(float(np.mean(res["ref0"])), 3), flush=True)
+    for k in knobs:
+        _lib.set_tuning(k, 1)
