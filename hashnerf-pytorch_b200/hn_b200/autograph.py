@@ -84,7 +84,7 @@ def shutdown() -> None:
 
 class _Entry:
     __slots__ = ("calls", "failed", "pending", "g_f", "g_b", "static_in", "keys", "outs", "diff_idx", "static_grads",
-                 "grad_is_zero", "sinks", "ptrs", "params", "slots")
+                 "grad_is_zero", "sinks", "ptrs", "params", "slots", "owners")
 
     def __init__(self):
         self.calls = 0
@@ -204,6 +204,8 @@ def render_rays(impl: Callable, ray_batch: torch.Tensor, kw: dict) -> Optional[d
         entry.slots = _param_slots(mods)
         if not entry.slots:
             return None            # nothing to train: not a training call
+        # the key holds ids: keep the objects alive as long as the entry, so that an id cannot be recycled into it
+        entry.owners = (tuple(mods), kw.get("network_query_fn"))
         _entries[key] = entry
     entry.calls += 1
     if entry.failed:
