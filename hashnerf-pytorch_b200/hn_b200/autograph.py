@@ -13,7 +13,10 @@ gradients enabled, its forward is captured into one CUDA graph and the backward 
 
 Parameter gradients are accumulated by the captured kernels straight into the modules' persistent GradSink
 buffers, as in the eager path.  Outputs are STATIC buffers: a call's results are overwritten by the next call with
-the same signature (a training loop consumes them within the iteration).
+the same signature (a training loop consumes them within the iteration).  The backward graph is captured per SET of
+outputs that actually received a gradient (first backward with a new set: the captured forward's autograd graph is
+run as it is; the graph for that set is captured before the next forward): outputs the loss does not use must not
+become roots with zero gradients -- an empty ray's disparity is NaN and 0 x NaN would poison its gradient.
 
 Two things make this safe under a foreign loop:
 * everything runs on ONE non-default stream that this module makes current (``ensure_stream``) and on which it
@@ -42,7 +45,7 @@ WARMUP_CALLS = 3          # eager calls per signature before the capture (lazy a
 
 _stream: Optional[torch.cuda.Stream] = None
 _entries: Dict[tuple, "_Entry"] = {}
-stats = {"captures": 0, "replays": 0, "eager": 0, "failed": 0}
+stats = {"captures": 0, "captures_bwd": 0, "replays": 0, "eager": 0, "failed": 0}
 
 
 def enable(on: bool = True) -> None:
@@ -83,14 +86,16 @@ def shutdown() -> None:
 
 
 class _Entry:
-    __slots__ = ("calls", "failed", "pending", "g_f", "g_b", "static_in", "keys", "outs", "diff_idx", "static_grads",
-                 "grad_is_zero", "sinks", "ptrs", "params", "slots", "owners")
+    __slots__ = ("calls", "failed", "pending", "g_f", "bwd", "want_bwd", "static_in", "keys", "outs", "diff_idx",
+                 "static_grads", "sinks", "ptrs", "params", "slots", "owners")
 
     def __init__(self):
         self.calls = 0
         self.failed = False
         self.pending = False
         self.g_f = None
+        self.bwd = {}
+        self.want_bwd = None
 
 
 def _modules_of(kw) -> List[torch.nn.Module]:
@@ -130,20 +135,37 @@ class _ReplayFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         entry = ctx.entry
-        for k, (buf, i) in enumerate(zip(entry.static_grads, entry.diff_idx)):
-            g = grads[i]
-            if g is None:            # an output the loss does not use: its buffer stays zero
-                if not entry.grad_is_zero[k]:
-                    buf.zero_()
-                    entry.grad_is_zero[k] = True
-            else:
-                buf.copy_(g, non_blocking=True)
-                entry.grad_is_zero[k] = False
+        # Only the outputs the caller's loss uses are roots of the backward pass.  (Feeding zeros for the others is
+        # NOT the same: an empty ray has acc = 0, its disparity is 1 / (depth / acc) = NaN, and 0 x NaN poisons the
+        # ray's gradient -- autograd never visits an output without a gradient, and neither does the eager path.)
+        used = tuple(i for i in entry.diff_idx if grads[i] is not None)
+        if not used:
+            entry.pending = False
+            return (None, None) + (None,) * len(entry.params)
+        for i in used:
+            entry.static_grads[i].copy_(grads[i], non_blocking=True)
         for s in entry.sinks:      # zero_grad(set_to_none=True) bookkeeping: re-attach param.grad, clear if needed
             s.acquire()
-        entry.g_b.replay()
+        g_b = entry.bwd.get(used)
+        if g_b is not None:
+            g_b.replay()
+        else:
+            # first backward with this set of outputs: run the captured forward's autograd graph as it is (its saved
+            # tensors are the static buffers the forward replay has just filled); render_rays() captures the graph
+            # for this set before the next forward
+            torch.autograd.backward([entry.outs[i] for i in used], [entry.static_grads[i] for i in used],
+                                    retain_graph=True)
+            entry.want_bwd = used
         entry.pending = False
         return (None, None) + (None,) * len(entry.params)
+
+
+def _capture_backward(entry: _Entry, used: tuple, stream) -> None:
+    g_b = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_b, stream=stream, pool=entry.g_f.pool()):
+        torch.autograd.backward([entry.outs[i] for i in used], [entry.static_grads[i] for i in used], retain_graph=True)
+    entry.bwd[used] = g_b
+    stats["captures_bwd"] = stats.get("captures_bwd", 0) + 1
 
 
 def _capture(entry: _Entry, impl: Callable, ray_batch: torch.Tensor, kw: dict, mods, params) -> None:
@@ -165,14 +187,11 @@ def _capture(entry: _Entry, impl: Callable, ray_batch: torch.Tensor, kw: dict, m
     diff_idx = [i for i, o in enumerate(outs) if o.requires_grad]
     if not diff_idx:
         raise RuntimeError("no differentiable output")
-    static_grads = [torch.zeros_like(outs[i]) for i in diff_idx]
-    g_b = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g_b, stream=stream, pool=g_f.pool()):
-        torch.autograd.backward([outs[i] for i in diff_idx], static_grads)
     sinks = _sinks_of(mods)    # the forward may have (re)created them
-    entry.g_f, entry.g_b = g_f, g_b
-    entry.keys, entry.outs, entry.diff_idx, entry.static_grads = keys, outs, diff_idx, static_grads
-    entry.grad_is_zero = [True] * len(static_grads)
+    entry.g_f = g_f
+    entry.keys, entry.outs, entry.diff_idx = keys, outs, diff_idx
+    entry.static_grads = {i: torch.zeros_like(outs[i]) for i in diff_idx}
+    entry.bwd, entry.want_bwd = {}, None
     entry.sinks, entry.params = sinks, params
     entry.ptrs = _pointers(params, sinks)
     stats["captures"] += 1
@@ -229,6 +248,21 @@ def render_rays(impl: Callable, ray_batch: torch.Tensor, kw: dict) -> Optional[d
         del _entries[key]          # parameters replaced or tensors moved: capture again after the next warm-up
         stats["eager"] += 1
         return None
+    if entry.want_bwd is not None and not entry.pending:
+        used, entry.want_bwd = entry.want_bwd, None
+        if used not in entry.bwd:
+            try:
+                for hook in ops.pre_capture_hooks:
+                    hook()
+                for s in entry.sinks:
+                    s.acquire()    # param.grad attached: the captured backward contains no zero-fill
+                _capture_backward(entry, used, torch.cuda.current_stream(ray_batch.device))
+            except Exception as exc:  # noqa: BLE001
+                del _entries[key]
+                stats["failed"] += 1
+                warnings.warn(f"hn_b200.autograph: backward capture failed ({type(exc).__name__}: {exc})")
+                torch.cuda.synchronize(ray_batch.device)
+                return None
     if entry.pending:              # the previous forward's backward has not run: do not clobber its activations
         entry.pending = False
         stats["eager"] += 1

@@ -34,6 +34,11 @@ def main(argv):
         k = rest.index("--iters")
         iters = int(rest[k + 1])
         del rest[k:k + 2]
+    seed = None
+    if "--seed" in rest:       # the script seeds numpy only (run_nerf.py:733): fix the parameter initialisation too
+        k = rest.index("--seed")
+        seed = int(rest[k + 1])
+        del rest[k:k + 2]
     os.makedirs(workdir, exist_ok=True)
     sys.path.insert(0, os.path.join(HERE))
     import make_scene
@@ -45,12 +50,16 @@ def main(argv):
             "dataset_type = blender", "no_batching = True", "use_viewdirs = True", "white_bkgd = True",
             "lrate_decay = 500", "N_samples = 32", "N_importance = 64", "N_rand = 512", "precrop_iters = 10",
             "precrop_frac = 0.5", "testskip = 1", "log2_hashmap_size = 14", "finest_res = 256", "lrate = 0.01",
-            f"i_print = 10", f"i_weights = {iters}", f"i_testset = {iters}", f"i_video = {iters}", "chunk = 8192", ""]))
+            f"i_print = 10", f"i_weights = {iters}", f"i_testset = {iters}", f"i_video = {iters}", "chunk = 8192"]
+            + (["perturb = 0."] if os.environ.get("HN_HARNESS_NO_PERTURB") == "1" else []) + [""]))
     ref = reference_root()
     os.environ["HN_HARNESS_ITERS"] = str(iters)
     sys.path[:0] = [os.path.join(HERE, "standins"), os.path.join(ROOT, "hashnerf-pytorch_b200"), ref]
     sys.argv = [os.path.join(ref, "run_nerf.py"), "--config", cfg] + rest
     os.chdir(workdir)
+    if seed is not None:
+        import torch
+        torch.manual_seed(seed)
     try:
         runpy.run_path(os.path.join(ref, "run_nerf.py"), run_name="__main__")
     finally:
