@@ -186,3 +186,20 @@ def test_helpers_import_surface():
     from embedding.embedder import Embedder, get_embedder  # noqa: F401  (reference import line :19)
     from loss import sigma_sparsity_loss, total_variation_loss  # noqa: F401
     assert float(h.mse2psnr(torch.tensor(0.01))) == pytest.approx(20.0, abs=1e-4)
+
+
+def test_autograph_is_opt_in_and_inert_without_cuda():
+    """hn_b200.autograph only acts when HN_AUTO_GRAPH=1 (or enable()) AND its side stream exists: by default, and on a
+    machine without CUDA, render_rays runs the eager statements and nothing switches streams."""
+    import inspect
+    import run_nerf_helpers as h
+    from hn_b200 import autograph
+    assert autograph.ENABLED is (os.environ.get("HN_AUTO_GRAPH", "0") == "1")
+    if not autograph.ENABLED:
+        assert autograph.ensure_stream("cuda") is None
+        assert autograph.render_rays(h._render_rays_eager, torch.zeros(4, 11), {}) is None
+    # the eager implementation keeps the public function's parameters (the wrapper forwards them by name)
+    pub = list(inspect.signature(h.render_rays).parameters)
+    assert list(inspect.signature(h._render_rays_eager).parameters) == pub
+    autograph.reset()
+    assert set(autograph.stats) >= {"captures", "captures_bwd", "replays", "eager", "failed"}
