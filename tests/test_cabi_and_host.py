@@ -203,3 +203,22 @@ def test_autograph_is_opt_in_and_inert_without_cuda():
     assert list(inspect.signature(h._render_rays_eager).parameters) == pub
     autograph.reset()
     assert set(autograph.stats) >= {"captures", "captures_bwd", "replays", "eager", "failed"}
+
+
+def test_sort_workspace_covers_both_layouts():
+    """hn_hash_sort_workspace_bytes is host arithmetic: it must cover the two-level layout (histogram, first slots,
+    one 32-byte sector per bin cursor, N float4 records) and the single-pass layout (one counter per cell, key and
+    rank per point), whichever the call ends up using."""
+    from hn_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.hn_hash_sort_workspace_bytes.restype = ctypes.c_int64
+    lib.hn_hash_sort_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int]
+    bins, stride = 16384, 8
+    for n, g in [(0, 1), (1, 8), (70_001, 32), (1 << 19, 64), (1 << 24, 256), (1 << 24, 300), (1000, 1024)]:
+        got = lib.hn_hash_sort_workspace_bytes(n, g)
+        two_level = (2 * (bins + 4) + bins * stride) * 4 + n * 16
+        single = (g ** 3 + (g ** 3 + 2047) // 2048 + 2 * n) * 4
+        assert got >= two_level and got >= single, (n, g, got, two_level, single)
+        assert got % 4 == 0
+    assert lib.hn_hash_sort_workspace_bytes(-1, 8) == -1 and lib.hn_hash_sort_workspace_bytes(8, 0) == -1
+    assert lib.hn_hash_sort_workspace_bytes(8, 1025) == -1
